@@ -1,0 +1,114 @@
+// common.cuh — constants, HBM record layouts and small device helpers shared by all kernels.
+//
+// Algorithm constants follow SURVEY.md Appendix A (the un-vendored upstream rasterizer
+// hbb1/diff-surfel-rasterization @ e0ed0207; its config lives in files absent from
+// /root/reference) and are kept in this one header, as SURVEY §7 asks.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace surfel {
+
+constexpr int kBlockX = 16;
+constexpr int kBlockY = 16;
+constexpr int kTilePixels = kBlockX * kBlockY;
+constexpr float kNear = 0.2f;
+constexpr float kFar = 100.0f;
+constexpr float kFilterSize = 0.707106f;
+constexpr float kFilterInvSquare = 2.0f;
+constexpr float kCutoff = 3.0f;
+constexpr float kAlphaMax = 0.99f;
+constexpr float kAlphaMin = 1.0f / 255.0f;
+constexpr float kTMin = 0.0001f;
+
+// out_others channel order (reference gaussian_renderer/__init__.py:118-135)
+constexpr int kChDepth = 0, kChAlpha = 1, kChNormal = 2, kChMidDepth = 5, kChDistortion = 6;
+
+// ---------------------------------------------------------------------------------------------
+// HBM layout of the per-splat state written by preprocess and gathered by render (fwd and bwd).
+// One 96-byte record = 3 full 32-byte sectors, 16-byte aligned, read with 128-bit loads:
+//   q0 = (Tu.x, Tu.y, Tu.z, Tv.x)      q1 = (Tv.y, Tv.z, Tw.x, Tw.y)
+//   q2 = (Tw.z, xy.x, xy.y, opacity)   q3 = (n.x, n.y, n.z, depth)
+//   q4 = (r, g, b, unused)             q5 = conservative screen bbox (x0, y0, x1, y1) of the
+//                                           region where alpha can reach 1/255 (render culling)
+// ---------------------------------------------------------------------------------------------
+constexpr int kRecQuads = 6;
+constexpr int kRecBytes = kRecQuads * 16;
+
+// Per-splat gradient record accumulated by render backward (float atomics), 20 floats = 80 B:
+//   [0..8] dL_dtransMat, [9..10] dL_dmean2D.xy, [11] dL_dopacity, [12..14] dL_dnormal,
+//   [15..17] dL_dcolor, [18..19] pad
+constexpr int kGradFloats = 20;
+
+struct GeomLayout {
+    size_t rec, tiles_touched, offsets, clamped, scan_status, counters, total;
+};
+struct ImageLayout {
+    size_t accum, n_contrib, total;  // accum: final_T, M1, M2 planes; n_contrib: last, median
+};
+struct BinningLayout {
+    size_t keys_a, keys_b, vals_a, vals_b, ranges, sort_temp, total;
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+constexpr int kPreBlock = 128;   // preprocess threads per block (and scan tile)
+
+inline GeomLayout geom_layout(int P) {
+    GeomLayout L;
+    size_t o = 0;
+    size_t p = (size_t)(P > 0 ? P : 1);
+    L.rec = o;            o = align_up(o + p * kRecBytes, 256);
+    L.tiles_touched = o;  o = align_up(o + p * 4, 256);
+    L.offsets = o;        o = align_up(o + p * 4, 256);
+    L.clamped = o;        o = align_up(o + p, 256);
+    L.scan_status = o;    o = align_up(o + ((p + kPreBlock - 1) / kPreBlock + 1) * 8, 256);
+    L.counters = o;       o = align_up(o + 64, 256);   // [0] ticket, [1] num_rendered
+    L.total = o;
+    return L;
+}
+inline ImageLayout image_layout(int W, int H) {
+    ImageLayout L;
+    size_t n = (size_t)W * (size_t)H;
+    size_t o = 0;
+    L.accum = o;      o = align_up(o + n * 3 * 4, 256);
+    L.n_contrib = o;  o = align_up(o + n * 2 * 4, 256);
+    L.total = o;
+    return L;
+}
+
+// float -> int32, truncate toward zero, saturating, NaN -> 0 (PTX cvt.rzi.s32.f32; the oracle's
+// f2i_sat() restates exactly this).
+__device__ __forceinline__ int f2i_sat(float x) { return __float2int_rz(x); }
+
+__device__ __forceinline__ void get_rect(float cx, float cy, int radius, int gx, int gy, int row0,
+                                         int row1, int& x0, int& y0, int& x1, int& y1) {
+    const float r = (float)radius;
+    x0 = min(gx, max(0, f2i_sat((cx - r) / (float)kBlockX)));
+    y0 = min(gy, max(0, f2i_sat((cy - r) / (float)kBlockY)));
+    x1 = min(gx, max(0, f2i_sat(((cx + r) + (float)(kBlockX - 1)) / (float)kBlockX)));
+    y1 = min(gy, max(0, f2i_sat(((cy + r) + (float)(kBlockY - 1)) / (float)kBlockY)));
+    y0 = min(row1, max(row0, y0));
+    y1 = min(row1, max(row0, y1));
+}
+
+__device__ __forceinline__ float4 ld_nc_f4(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+}  // namespace surfel
+
+// Error plumbing shared by the C-ABI translation units.
+void surfel_set_error(const char* fmt, ...);
+#define SURFEL_CUDA_OK(expr)                                                              \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            surfel_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                             __FILE__, __LINE__);                                         \
+            return 1;                                                                     \
+        }                                                                                 \
+    } while (0)

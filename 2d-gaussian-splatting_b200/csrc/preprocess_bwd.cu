@@ -1,0 +1,200 @@
+// preprocess_bwd.cu — per-splat backward of the preprocess.
+//
+// Replaces upstream preprocessCUDA backward with its helpers compute_transmat_aabb vjp,
+// quat_to_rotmat_vjp and SH backward (algorithm SURVEY Appendix A.5):
+//   1. fold dL_dmean2D (low-pass branch) into dL_dT through the AABB-centre formula,
+//   2. dL_dT -> dL_dmean3D, dL_dscale, dL_dq (unit quaternion) and the normal's vjp,
+//   3. SH backward (dL_dsh, and dL_dmean3D through the view direction),
+//   4. overwrite dL_dmean2D with the densification proxy dL_dT[2|5] * depth * 0.5 * (W|H).
+// The kernel writes EVERY output row (zeros for culled splats), so the caller can hand in
+// uninitialised tensors: no separate zero-fill pass over the 59 floats/splat of gradients.
+// Kept quirk: dL_dscale ignores scale_modifier (only the viewer uses modifier != 1).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace surfel {
+
+__constant__ float b_SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                 -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float b_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                 0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                 -0.5900435899266435f};
+constexpr float SH_C0 = 0.28209479177387814f;
+constexpr float SH_C1 = 0.4886025119029199f;
+
+__global__ void __launch_bounds__(128) preprocess_bwd_kernel(PreBwdParams p) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= p.P) return;
+    const bool visible = p.radii[idx] > 0;
+    const bool geom = p.transMat_precomp == nullptr;
+    const bool has_sh = !p.has_colors_precomp && p.shs != nullptr;
+
+    float gT[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    float gm2x = 0, gm2y = 0, gopa = 0, gn[3] = {0, 0, 0}, gc[3] = {0, 0, 0};
+    float tm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    float g3[3] = {0, 0, 0}, gs[2] = {0, 0}, gq[4] = {0, 0, 0, 0};
+    float px = 0, py = 0, pz = 0;
+
+    if (visible) {
+        const float4* gr = reinterpret_cast<const float4*>(p.grad_rec + (size_t)idx * kGradFloats);
+        const float4 a = gr[0], b = gr[1], c = gr[2], d = gr[3], e = gr[4];
+        gT[0] = a.x; gT[1] = a.y; gT[2] = a.z; gT[3] = a.w; gT[4] = b.x; gT[5] = b.y; gT[6] = b.z; gT[7] = b.w;
+        gT[8] = c.x; gm2x = c.y; gm2y = c.z; gopa = c.w;
+        gn[0] = d.x; gn[1] = d.y; gn[2] = d.z; gc[0] = d.w; gc[1] = e.x; gc[2] = e.y;
+        const float4* r = p.rec + (size_t)idx * kRecQuads;
+        const float4 q0 = r[0], q1 = r[1], q2 = r[2];
+        tm[0] = q0.x; tm[1] = q0.y; tm[2] = q0.z; tm[3] = q0.w; tm[4] = q1.x; tm[5] = q1.y;
+        tm[6] = q1.z; tm[7] = q1.w; tm[8] = q2.x;
+
+        // 1. AABB-centre vjp
+        if (gm2x != 0.0f || gm2y != 0.0f) {
+            const float t[3] = {kCutoff * kCutoff, kCutoff * kCutoff, -1.0f};
+            const float dd = t[0] * tm[6] * tm[6] + t[1] * tm[7] * tm[7] + t[2] * tm[8] * tm[8];
+            float f[3], dT3[3], dot = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                f[k] = t[k] / dd;
+                gT[k] += gm2x * f[k] * tm[6 + k];
+                gT[3 + k] += gm2y * f[k] * tm[6 + k];
+                dT3[k] = gm2x * f[k] * tm[k] + gm2y * f[k] * tm[3 + k];
+                dot += (gm2x * tm[k] * tm[6 + k] + gm2y * tm[3 + k] * tm[6 + k]) * f[k];
+            }
+            const float dL_dd = dot * (-1.0f / dd);
+#pragma unroll
+            for (int k = 0; k < 3; k++) gT[6 + k] += dT3[k] + dL_dd * (t[k] * tm[6 + k] * 2.0f);
+        }
+
+        px = p.means3D[3 * (size_t)idx]; py = p.means3D[3 * (size_t)idx + 1]; pz = p.means3D[3 * (size_t)idx + 2];
+        if (geom) {
+            const float* vm = p.viewmatrix;
+            const float* pr = p.projmatrix;
+            const float hw = (float)p.W / 2.0f, hh = (float)p.H / 2.0f;
+            const float cw = (float)(p.W - 1) / 2.0f, ch = (float)(p.H - 1) / 2.0f;
+            const float4 q = reinterpret_cast<const float4*>(p.rotations)[idx];
+            const float2 sc = reinterpret_cast<const float2*>(p.scales)[idx];
+            const float inv = 1.0f / sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+            const float w = q.x * inv, x = q.y * inv, y = q.z * inv, z = q.w * inv;
+            float R[3][3];
+            R[0][0] = 1.0f - 2.0f * (y * y + z * z); R[0][1] = 2.0f * (x * y - w * z); R[0][2] = 2.0f * (x * z + w * y);
+            R[1][0] = 2.0f * (x * y + w * z); R[1][1] = 1.0f - 2.0f * (x * x + z * z); R[1][2] = 2.0f * (y * z - w * x);
+            R[2][0] = 2.0f * (x * z - w * y); R[2][1] = 2.0f * (y * z + w * x); R[2][2] = 1.0f - 2.0f * (x * x + y * y);
+            // dRows[i][k] = sum_j gT[3j+i] * Pm[k][j]
+            float dRows[3][3];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const float Pm0 = pr[4 * k + 0] * hw + pr[4 * k + 3] * cw;
+                const float Pm1 = pr[4 * k + 1] * hh + pr[4 * k + 3] * ch;
+                const float Pm2 = pr[4 * k + 3];
+#pragma unroll
+                for (int i = 0; i < 3; i++) dRows[i][k] = gT[i] * Pm0 + gT[3 + i] * Pm1 + gT[6 + i] * Pm2;
+            }
+            float dtn[3];
+#pragma unroll
+            for (int r2 = 0; r2 < 3; r2++) dtn[r2] = vm[4 * r2 + 0] * gn[0] + vm[4 * r2 + 1] * gn[1] + vm[4 * r2 + 2] * gn[2];
+            // dual-visible sign, recomputed as in the forward
+            const float L2[3] = {R[0][2], R[1][2], R[2][2]};
+            const float nv0 = vm[0] * L2[0] + vm[4] * L2[1] + vm[8] * L2[2];
+            const float nv1 = vm[1] * L2[0] + vm[5] * L2[1] + vm[9] * L2[2];
+            const float nv2 = vm[2] * L2[0] + vm[6] * L2[1] + vm[10] * L2[2];
+            const float pvx = vm[0] * px + vm[4] * py + vm[8] * pz + vm[12];
+            const float pvy = vm[1] * px + vm[5] * py + vm[9] * pz + vm[13];
+            const float pvz = vm[2] * px + vm[6] * py + vm[10] * pz + vm[14];
+            const float cs = -(pvx * nv0 + pvy * nv1 + pvz * nv2);
+            const float mult = cs > 0.0f ? 1.0f : -1.0f;
+            float v[3][3];   // v[c][r] = dL/dR[r][c]
+#pragma unroll
+            for (int r2 = 0; r2 < 3; r2++) {
+                v[0][r2] = dRows[0][r2] * sc.x; v[1][r2] = dRows[1][r2] * sc.y; v[2][r2] = dtn[r2] * mult;
+            }
+            gs[0] = dRows[0][0] * R[0][0] + dRows[0][1] * R[1][0] + dRows[0][2] * R[2][0];
+            gs[1] = dRows[1][0] * R[0][1] + dRows[1][1] * R[1][1] + dRows[1][2] * R[2][1];
+            gq[0] = 2.0f * (x * (v[1][2] - v[2][1]) + y * (v[2][0] - v[0][2]) + z * (v[0][1] - v[1][0]));
+            gq[1] = 2.0f * (-2.0f * x * (v[1][1] + v[2][2]) + y * (v[0][1] + v[1][0]) + z * (v[0][2] + v[2][0]) + w * (v[1][2] - v[2][1]));
+            gq[2] = 2.0f * (x * (v[0][1] + v[1][0]) - 2.0f * y * (v[0][0] + v[2][2]) + z * (v[1][2] + v[2][1]) + w * (v[2][0] - v[0][2]));
+            gq[3] = 2.0f * (x * (v[0][2] + v[2][0]) + y * (v[1][2] + v[2][1]) - 2.0f * z * (v[0][0] + v[1][1]) + w * (v[0][1] - v[1][0]));
+            g3[0] = dRows[2][0]; g3[1] = dRows[2][1]; g3[2] = dRows[2][2];
+        }
+    }
+
+    // 3. SH backward (writes the full dL_dsh row; zeros when culled / beyond the active degree)
+    if (has_sh) {
+        float* gsh = p.dL_dsh + (size_t)idx * 3 * p.M;
+        const int ncoef_active = visible ? (p.D + 1) * (p.D + 1) : 0;
+        if (visible) {
+            const float* sh = p.shs + (size_t)idx * 3 * p.M;
+            const uint8_t cb = p.clamped[idx];
+            const float dR[3] = {(cb & 1) ? 0.0f : gc[0], (cb & 2) ? 0.0f : gc[1], (cb & 4) ? 0.0f : gc[2]};
+            const float dox = px - p.campos[0], doy = py - p.campos[1], doz = pz - p.campos[2];
+            const float sq = dox * dox + doy * doy + doz * doz;
+            const float invl = 1.0f / sqrtf(sq);
+            const float x = dox * invl, y = doy * invl, z = doz * invl;
+            float ddx = 0, ddy = 0, ddz = 0;
+#define GS(i, val) do { const float _v = (val); gsh[3 * (i)] = _v * dR[0]; gsh[3 * (i) + 1] = _v * dR[1]; gsh[3 * (i) + 2] = _v * dR[2]; } while (0)
+#define DOT(i) (dR[0] * sh[3 * (i)] + dR[1] * sh[3 * (i) + 1] + dR[2] * sh[3 * (i) + 2])
+            GS(0, SH_C0);
+            if (p.D > 0) {
+                GS(1, -SH_C1 * y); GS(2, SH_C1 * z); GS(3, -SH_C1 * x);
+                ddx += -SH_C1 * DOT(3); ddy += -SH_C1 * DOT(1); ddz += SH_C1 * DOT(2);
+                if (p.D > 1) {
+                    const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                    GS(4, b_SH_C2[0] * xy); GS(5, b_SH_C2[1] * yz); GS(6, b_SH_C2[2] * (2.0f * zz - xx - yy));
+                    GS(7, b_SH_C2[3] * xz); GS(8, b_SH_C2[4] * (xx - yy));
+                    const float d4 = DOT(4), d5 = DOT(5), d6 = DOT(6), d7 = DOT(7), d8 = DOT(8);
+                    ddx += b_SH_C2[0] * y * d4 + b_SH_C2[2] * 2.0f * -x * d6 + b_SH_C2[3] * z * d7 + b_SH_C2[4] * 2.0f * x * d8;
+                    ddy += b_SH_C2[0] * x * d4 + b_SH_C2[1] * z * d5 + b_SH_C2[2] * 2.0f * -y * d6 + b_SH_C2[4] * 2.0f * -y * d8;
+                    ddz += b_SH_C2[1] * y * d5 + b_SH_C2[2] * 4.0f * z * d6 + b_SH_C2[3] * x * d7;
+                    if (p.D > 2) {
+                        GS(9, b_SH_C3[0] * y * (3.0f * xx - yy)); GS(10, b_SH_C3[1] * xy * z);
+                        GS(11, b_SH_C3[2] * y * (4.0f * zz - xx - yy));
+                        GS(12, b_SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy));
+                        GS(13, b_SH_C3[4] * x * (4.0f * zz - xx - yy)); GS(14, b_SH_C3[5] * z * (xx - yy));
+                        GS(15, b_SH_C3[6] * x * (xx - 3.0f * yy));
+                        const float d9 = DOT(9), d10 = DOT(10), d11 = DOT(11), d12 = DOT(12), d13 = DOT(13), d14 = DOT(14), d15 = DOT(15);
+                        ddx += b_SH_C3[0] * d9 * 6.0f * xy + b_SH_C3[1] * d10 * yz + b_SH_C3[2] * d11 * -2.0f * xy +
+                               b_SH_C3[3] * d12 * -6.0f * xz + b_SH_C3[4] * d13 * (-3.0f * xx + 4.0f * zz - yy) +
+                               b_SH_C3[5] * d14 * 2.0f * xz + b_SH_C3[6] * d15 * 3.0f * (xx - yy);
+                        ddy += b_SH_C3[0] * d9 * 3.0f * (xx - yy) + b_SH_C3[1] * d10 * xz +
+                               b_SH_C3[2] * d11 * (-3.0f * yy + 4.0f * zz - xx) + b_SH_C3[3] * d12 * -6.0f * yz +
+                               b_SH_C3[4] * d13 * -2.0f * xy + b_SH_C3[5] * d14 * -2.0f * yz + b_SH_C3[6] * d15 * -6.0f * xy;
+                        ddz += b_SH_C3[1] * d10 * xy + b_SH_C3[2] * d11 * 8.0f * yz +
+                               b_SH_C3[3] * d12 * 3.0f * (2.0f * zz - xx - yy) + b_SH_C3[4] * d13 * 8.0f * xz +
+                               b_SH_C3[5] * d14 * (xx - yy);
+                    }
+                }
+            }
+#undef GS
+#undef DOT
+            const float inv3 = invl * invl * invl;
+            g3[0] += ((doy * doy + doz * doz) * ddx - doy * dox * ddy - doz * dox * ddz) * inv3;
+            g3[1] += (-dox * doy * ddx + (dox * dox + doz * doz) * ddy - doz * doy * ddz) * inv3;
+            g3[2] += (-dox * doz * ddx - doy * doz * ddy + (dox * dox + doy * doy) * ddz) * inv3;
+        }
+        for (int i = 3 * ncoef_active; i < 3 * p.M; i++) gsh[i] = 0.0f;
+    }
+
+    // 4. outputs (every row written)
+    float* o;
+    o = p.dL_dmeans2D + 3 * (size_t)idx;
+    o[0] = visible ? gT[2] * tm[8] * 0.5f * (float)p.W : 0.0f;
+    o[1] = visible ? gT[5] * tm[8] * 0.5f * (float)p.H : 0.0f;
+    o[2] = 0.0f;
+    p.dL_dopacity[idx] = gopa;
+    o = p.dL_dmeans3D + 3 * (size_t)idx; o[0] = g3[0]; o[1] = g3[1]; o[2] = g3[2];
+    if (p.dL_dcolors) { o = p.dL_dcolors + 3 * (size_t)idx; o[0] = gc[0]; o[1] = gc[1]; o[2] = gc[2]; }
+    if (p.dL_dtransMat) {
+        o = p.dL_dtransMat + 9 * (size_t)idx;
+#pragma unroll
+        for (int k = 0; k < 9; k++) o[k] = gT[k];
+    }
+    if (p.dL_dscales) { o = p.dL_dscales + 2 * (size_t)idx; o[0] = gs[0]; o[1] = gs[1]; }
+    if (p.dL_drots) { o = p.dL_drots + 4 * (size_t)idx; o[0] = gq[0]; o[1] = gq[1]; o[2] = gq[2]; o[3] = gq[3]; }
+}
+
+int launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t stream) {
+    if (p.P <= 0) return 0;
+    preprocess_bwd_kernel<<<(p.P + 127) / 128, 128, 0, stream>>>(p);
+    SURFEL_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace surfel

@@ -1,0 +1,357 @@
+// preprocess_fwd.cu — per-splat forward preprocess FUSED with the tile-count prefix scan.
+//
+// Replaces upstream preprocessCUDA (forward) + cub::DeviceScan::InclusiveSum (SURVEY §8a rows
+// a6, a7; algorithm: SURVEY Appendix A.1/A.2).  One thread per splat:
+//   near cull -> splat->pixel homography T (in-tree restatement:
+//   /root/reference/gaussian_renderer/__init__.py:64-75) -> view-space normal + dual-visible flip
+//   -> AABB centre/extent -> radius -> tile rect -> SH->RGB (/root/reference/utils/sh_utils.py:57-112)
+// then a block scan of tiles_touched chained across blocks with a decoupled look-back, so the
+// inclusive offsets and the instance count R come out of the same launch (no separate scan
+// kernel, no second pass over tiles_touched).
+//
+// B200 notes: SH rows (192 B/splat, AoS) are the dominant HBM stream.  Only rows of splats that
+// survive culling are fetched, warp-cooperatively with 128-bit loads into padded shared memory
+// (conflict-free 13-quad stride), instead of upstream's per-thread stride-192 scalar reads.
+//
+// PARITY: this TU is compiled with -fmad=false and evaluates every expression in the order the
+// oracle (oracle/surfel_oracle.c) documents, so radii / rects / tiles_touched / depth bits are
+// bit-identical to the CPU restatement.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace surfel {
+
+__constant__ float c_SH_C2[5] = {1.0925484305920792f, -1.0925484305920792f, 0.31539156525252005f,
+                                 -1.0925484305920792f, 0.5462742152960396f};
+__constant__ float c_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.4570457994644658f,
+                                 0.3731763325901154f,  -0.4570457994644658f, 1.445305721320277f,
+                                 -0.5900435899266435f};
+constexpr float SH_C0 = 0.28209479177387814f;
+constexpr float SH_C1 = 0.4886025119029199f;
+
+constexpr unsigned long long kFlagAgg = 1ull << 32, kFlagPrefix = 2ull << 32;
+
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ float sh_eval_channel(const float* sh, int c, int D, float x, float y, float z) {
+#define S(i) sh[3 * (i) + c]
+    float r = SH_C0 * S(0);
+    if (D > 0) {
+        r = r - SH_C1 * y * S(1) + SH_C1 * z * S(2) - SH_C1 * x * S(3);
+        if (D > 1) {
+            float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+            r = r + c_SH_C2[0] * xy * S(4) + c_SH_C2[1] * yz * S(5) +
+                c_SH_C2[2] * (2.0f * zz - xx - yy) * S(6) + c_SH_C2[3] * xz * S(7) +
+                c_SH_C2[4] * (xx - yy) * S(8);
+            if (D > 2) {
+                r = r + c_SH_C3[0] * y * (3.0f * xx - yy) * S(9) + c_SH_C3[1] * xy * z * S(10) +
+                    c_SH_C3[2] * y * (4.0f * zz - xx - yy) * S(11) +
+                    c_SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy) * S(12) +
+                    c_SH_C3[4] * x * (4.0f * zz - xx - yy) * S(13) + c_SH_C3[5] * z * (xx - yy) * S(14) +
+                    c_SH_C3[6] * x * (xx - 3.0f * yy) * S(15);
+            }
+        }
+    }
+#undef S
+    return r;
+}
+
+constexpr int kShRowQuads = 13;                 // 12 data quads + 1 pad: conflict-free LDS.128
+constexpr int kShRowFloatsScalar = 49;          // scalar path stride (odd: conflict-free LDS.32)
+
+template <bool kVec4>
+__global__ void __launch_bounds__(kPreBlock) preprocess_fwd_kernel(PreFwdParams p) {
+    __shared__ float4 s_sh[(kPreBlock / 32) * 32 * kShRowQuads];
+    __shared__ int s_rows[kPreBlock];            // per warp: compacted list of visible lanes
+    __shared__ uint32_t s_warp_sum[kPreBlock / 32];
+    __shared__ uint32_t s_bid, s_excl;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_bid = atomicAdd(&p.counters[0], 1u);   // ticket => forward progress of look-back
+    __syncthreads();
+    const uint32_t bid = s_bid;
+    const int idx = (int)(bid * kPreBlock) + tid;
+
+    bool visible = false;
+    uint32_t tt = 0;
+    float tm[9], nrm[3] = {0, 0, 0}, cx = 0, cy = 0, pvz = 0, opa = 0;
+    int radius_i = 0;
+    float px = 0, py = 0, pz = 0;
+    const float* vm = p.viewmatrix;
+
+    if (idx < p.P) {
+        px = p.means3D[3 * (size_t)idx + 0];
+        py = p.means3D[3 * (size_t)idx + 1];
+        pz = p.means3D[3 * (size_t)idx + 2];
+        const float pvx = ((vm[0] * px + vm[4] * py) + vm[8] * pz) + vm[12];
+        const float pvy = ((vm[1] * px + vm[5] * py) + vm[9] * pz) + vm[13];
+        pvz = ((vm[2] * px + vm[6] * py) + vm[10] * pz) + vm[14];
+        if (pvz > kNear) {
+            // per-view Pm = projmatrix * ndc2pix (columns x*w, y*w, w)
+            const float hw = (float)p.W / 2.0f, hh = (float)p.H / 2.0f;
+            const float cw = (float)(p.W - 1) / 2.0f, ch = (float)(p.H - 1) / 2.0f;
+            if (p.transMat_precomp == nullptr) {
+                const float4 q = reinterpret_cast<const float4*>(p.rotations)[idx];
+                const float2 sc = reinterpret_cast<const float2*>(p.scales)[idx];
+                const float n2 = ((q.x * q.x + q.y * q.y) + q.z * q.z) + q.w * q.w;
+                const float inv = 1.0f / sqrtf(n2);
+                const float w = q.x * inv, x = q.y * inv, y = q.z * inv, z = q.w * inv;
+                const float R00 = 1.0f - 2.0f * (y * y + z * z), R01 = 2.0f * (x * y - w * z), R02 = 2.0f * (x * z + w * y);
+                const float R10 = 2.0f * (x * y + w * z), R11 = 1.0f - 2.0f * (x * x + z * z), R12 = 2.0f * (y * z - w * x);
+                const float R20 = 2.0f * (x * z - w * y), R21 = 2.0f * (y * z + w * x), R22 = 1.0f - 2.0f * (x * x + y * y);
+                const float su = p.scale_modifier * sc.x, sv = p.scale_modifier * sc.y;
+                const float L0[3] = {R00 * su, R10 * su, R20 * su};
+                const float L1[3] = {R01 * sv, R11 * sv, R21 * sv};
+                const float L2[3] = {R02, R12, R22};
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    float Pm0, Pm1, Pm2, Pm3;
+                    const float* pr = p.projmatrix;
+                    if (j == 0) {
+                        Pm0 = pr[0] * hw + pr[3] * cw; Pm1 = pr[4] * hw + pr[7] * cw;
+                        Pm2 = pr[8] * hw + pr[11] * cw; Pm3 = pr[12] * hw + pr[15] * cw;
+                    } else if (j == 1) {
+                        Pm0 = pr[1] * hh + pr[3] * ch; Pm1 = pr[5] * hh + pr[7] * ch;
+                        Pm2 = pr[9] * hh + pr[11] * ch; Pm3 = pr[13] * hh + pr[15] * ch;
+                    } else {
+                        Pm0 = pr[3]; Pm1 = pr[7]; Pm2 = pr[11]; Pm3 = pr[15];
+                    }
+                    tm[3 * j + 0] = (L0[0] * Pm0 + L0[1] * Pm1) + L0[2] * Pm2;
+                    tm[3 * j + 1] = (L1[0] * Pm0 + L1[1] * Pm1) + L1[2] * Pm2;
+                    tm[3 * j + 2] = ((px * Pm0 + py * Pm1) + pz * Pm2) + Pm3;
+                }
+                nrm[0] = (vm[0] * L2[0] + vm[4] * L2[1]) + vm[8] * L2[2];
+                nrm[1] = (vm[1] * L2[0] + vm[5] * L2[1]) + vm[9] * L2[2];
+                nrm[2] = (vm[2] * L2[0] + vm[6] * L2[1]) + vm[10] * L2[2];
+            } else {
+#pragma unroll
+                for (int k = 0; k < 9; k++) tm[k] = p.transMat_precomp[9 * (size_t)idx + k];
+                nrm[0] = 0.0f; nrm[1] = 0.0f; nrm[2] = 1.0f;
+            }
+            const float c = -((pvx * nrm[0] + pvy * nrm[1]) + pvz * nrm[2]);
+            if (c != 0.0f) {
+                const float mult = c > 0.0f ? 1.0f : -1.0f;
+                nrm[0] *= mult; nrm[1] *= mult; nrm[2] *= mult;
+                const float t0 = kCutoff * kCutoff, t1 = kCutoff * kCutoff, t2 = -1.0f;
+                const float d = (t0 * (tm[6] * tm[6]) + t1 * (tm[7] * tm[7])) + t2 * (tm[8] * tm[8]);
+                if (d != 0.0f) {
+                    const float f0 = t0 / d, f1 = t1 / d, f2 = t2 / d;
+                    cx = (f0 * (tm[0] * tm[6]) + f1 * (tm[1] * tm[7])) + f2 * (tm[2] * tm[8]);
+                    cy = (f0 * (tm[3] * tm[6]) + f1 * (tm[4] * tm[7])) + f2 * (tm[5] * tm[8]);
+                    const float ex = (f0 * (tm[0] * tm[0]) + f1 * (tm[1] * tm[1])) + f2 * (tm[2] * tm[2]);
+                    const float ey = (f0 * (tm[3] * tm[3]) + f1 * (tm[4] * tm[4])) + f2 * (tm[5] * tm[5]);
+                    const float hx = sqrtf(fmaxf(1e-4f, cx * cx - ex));
+                    const float hy = sqrtf(fmaxf(1e-4f, cy * cy - ey));
+                    const float radius = ceilf(fmaxf(fmaxf(hx, hy), kCutoff * kFilterSize));
+                    if (radius == radius && cx == cx && cy == cy) {
+                        radius_i = f2i_sat(radius);
+                        int x0, y0, x1, y1;
+                        get_rect(cx, cy, radius_i, p.gx, p.gy, p.row0, p.row1, x0, y0, x1, y1);
+                        tt = (uint32_t)((x1 - x0) * (y1 - y0));
+                        visible = tt != 0;
+                    }
+                }
+            }
+        }
+        if (visible) opa = p.opacities[idx];
+    }
+
+    // ---- SH -> RGB for surviving splats (rows staged warp-cooperatively) ----
+    float rgb[3] = {0, 0, 0};
+    unsigned clamp_bits = 0;
+    const unsigned vis_mask = __ballot_sync(0xffffffffu, visible);
+    if (p.colors_precomp == nullptr) {
+        if (vis_mask) {
+            int* rows = s_rows + warp * 32;
+            const int nvis = __popc(vis_mask);
+            if (visible) rows[__popc(vis_mask & ((1u << lane) - 1u))] = lane;
+            __syncwarp();
+            const int warp_base = (int)(bid * kPreBlock) + warp * 32;
+            float sh[48];
+            if (kVec4) {
+                float4* dst = s_sh + warp * 32 * kShRowQuads;
+                const float4* src = reinterpret_cast<const float4*>(p.shs);
+                for (int f = lane; f < nvis * 12; f += 32) {
+                    const int slot = f / 12, q = f - slot * 12;
+                    const int row = rows[slot];
+                    dst[row * kShRowQuads + q] = ld_nc_f4(src + (size_t)(warp_base + row) * 12 + q);
+                }
+                __syncwarp();
+                if (visible) {
+#pragma unroll
+                    for (int q = 0; q < 12; q++) {
+                        const float4 v = dst[lane * kShRowQuads + q];
+                        sh[4 * q + 0] = v.x; sh[4 * q + 1] = v.y; sh[4 * q + 2] = v.z; sh[4 * q + 3] = v.w;
+                    }
+                }
+            } else {
+                float* dst = reinterpret_cast<float*>(s_sh) + warp * 32 * 52;
+                const int ncoef = 3 * (p.D + 1) * (p.D + 1);
+                const size_t row_stride = (size_t)3 * p.M;
+                for (int f = lane; f < nvis * ncoef; f += 32) {
+                    const int slot = f / ncoef, q = f - slot * ncoef;
+                    const int row = rows[slot];
+                    dst[row * kShRowFloatsScalar + q] = p.shs[(size_t)(warp_base + row) * row_stride + q];
+                }
+                __syncwarp();
+                if (visible) {
+#pragma unroll
+                    for (int q = 0; q < 48; q++) sh[q] = q < ncoef ? dst[lane * kShRowFloatsScalar + q] : 0.0f;
+                }
+            }
+            if (visible) {
+                float dx = px - p.campos[0], dy = py - p.campos[1], dz = pz - p.campos[2];
+                const float len = sqrtf((dx * dx + dy * dy) + dz * dz);
+                dx = dx / len; dy = dy / len; dz = dz / len;
+#pragma unroll
+                for (int ch = 0; ch < 3; ch++) {
+                    const float v = sh_eval_channel(sh, ch, p.D, dx, dy, dz) + 0.5f;
+                    if (v < 0.0f) clamp_bits |= 1u << ch;
+                    rgb[ch] = fmaxf(v, 0.0f);
+                }
+            }
+        }
+    } else if (visible) {
+        rgb[0] = p.colors_precomp[3 * (size_t)idx + 0];
+        rgb[1] = p.colors_precomp[3 * (size_t)idx + 1];
+        rgb[2] = p.colors_precomp[3 * (size_t)idx + 2];
+    }
+
+    // ---- write per-splat state ----
+    if (idx < p.P) {
+        p.radii[idx] = visible ? radius_i : 0;
+        p.tiles_touched[idx] = tt;
+        p.clamped[idx] = (uint8_t)clamp_bits;
+        if (visible) {
+            // conservative screen bbox of {alpha >= 1/255}: low-pass disk around xy, united with the
+            // projected ellipse rho3d <= tau when it is bounded (render culling).
+            float bx0, by0, bx1, by1;
+            const float a255 = 255.0f * opa;
+            if (a255 < 0.999f) {
+                bx0 = by0 = 3.0e38f; bx1 = by1 = -3.0e38f;     // can never reach 1/255: empty box
+            } else {
+                const float tau = 2.0f * logf(a255) + 0.01f;
+                const float r2 = sqrtf(0.5f * tau) + 0.05f;
+                bx0 = cx - r2; bx1 = cx + r2; by0 = cy - r2; by1 = cy + r2;
+                const float wxy = tm[6] * tm[6] + tm[7] * tm[7];
+                const float wz2 = tm[8] * tm[8];
+                if (tm[8] > 0.0f && wz2 > 1.05f * tau * wxy) {
+                    const float d = tau * wxy - wz2;
+                    const float f0 = tau / d, f2 = -1.0f / d;
+                    const float ecx = f0 * (tm[0] * tm[6] + tm[1] * tm[7]) + f2 * (tm[2] * tm[8]);
+                    const float ecy = f0 * (tm[3] * tm[6] + tm[4] * tm[7]) + f2 * (tm[5] * tm[8]);
+                    const float eex = f0 * (tm[0] * tm[0] + tm[1] * tm[1]) + f2 * (tm[2] * tm[2]);
+                    const float eey = f0 * (tm[3] * tm[3] + tm[4] * tm[4]) + f2 * (tm[5] * tm[5]);
+                    const float ehx = sqrtf(fmaxf(0.0f, ecx * ecx - eex));
+                    const float ehy = sqrtf(fmaxf(0.0f, ecy * ecy - eey));
+                    const float mx = 0.05f + 1e-4f * (fabsf(ecx) + ehx);
+                    const float my = 0.05f + 1e-4f * (fabsf(ecy) + ehy);
+                    bx0 = fminf(bx0, ecx - ehx - mx); bx1 = fmaxf(bx1, ecx + ehx + mx);
+                    by0 = fminf(by0, ecy - ehy - my); by1 = fmaxf(by1, ecy + ehy + my);
+                    if (!(ecx == ecx) || !(ecy == ecy) || !(ehx == ehx) || !(ehy == ehy)) {
+                        bx0 = by0 = -3.0e38f; bx1 = by1 = 3.0e38f;
+                    }
+                } else {
+                    bx0 = by0 = -3.0e38f; bx1 = by1 = 3.0e38f;  // unbounded conic: never culled
+                }
+            }
+            float4* r = p.rec + (size_t)idx * kRecQuads;
+            r[0] = make_float4(tm[0], tm[1], tm[2], tm[3]);
+            r[1] = make_float4(tm[4], tm[5], tm[6], tm[7]);
+            r[2] = make_float4(tm[8], cx, cy, opa);
+            r[3] = make_float4(nrm[0], nrm[1], nrm[2], pvz);
+            r[4] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+            r[5] = make_float4(bx0, by0, bx1, by1);
+        }
+    }
+
+    // ---- block inclusive scan of tiles_touched + decoupled look-back across blocks ----
+    uint32_t incl = tt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp_sum[warp] = incl;
+    __syncthreads();
+    uint32_t warp_excl = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < kPreBlock / 32; w++) {
+        const uint32_t s = s_warp_sum[w];
+        if (w < warp) warp_excl += s;
+        block_total += s;
+    }
+    if (warp == 0) {
+        unsigned long long* status = p.scan_status;
+        uint32_t excl = 0;
+        if (bid == 0) {
+            if (lane == 0) st_status(status + 0, kFlagPrefix | block_total);
+        } else {
+            if (lane == 0) st_status(status + bid, kFlagAgg | block_total);
+            int look = (int)bid - 1;
+            while (true) {
+                const int j = look - lane;
+                unsigned long long s = kFlagPrefix;
+                if (j >= 0) {
+                    s = ld_status(status + j);
+                    while ((s >> 32) == 0) s = ld_status(status + j);
+                }
+                const unsigned pm = __ballot_sync(0xffffffffu, (s >> 32) == 2ull);
+                const int first = pm ? (__ffs(pm) - 1) : 32;
+                uint32_t v = (lane <= first) ? (uint32_t)(s & 0xffffffffull) : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                excl += v;
+                if (pm) break;
+                look -= 32;
+            }
+            if (lane == 0) st_status(status + bid, kFlagPrefix | (unsigned long long)(excl + block_total));
+        }
+        if (lane == 0) {
+            s_excl = excl;
+            if (bid == gridDim.x - 1) p.counters[1] = excl + block_total;   // R = num_rendered
+        }
+    }
+    __syncthreads();
+    if (idx < p.P) p.offsets[idx] = s_excl + warp_excl + incl;
+}
+
+// markVisible: near-plane test only (SURVEY §2.2 checkFrustum).
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D,
+                                    const float* __restrict__ vm, uint8_t* __restrict__ present) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= P) return;
+    const float px = means3D[3 * (size_t)idx], py = means3D[3 * (size_t)idx + 1], pz = means3D[3 * (size_t)idx + 2];
+    const float pvz = ((vm[2] * px + vm[6] * py) + vm[10] * pz) + vm[14];
+    present[idx] = (uint8_t)(pvz > kNear);
+}
+
+int launch_preprocess_fwd(const PreFwdParams& p, cudaStream_t stream) {
+    if (p.P <= 0) return 0;
+    const int blocks = (p.P + kPreBlock - 1) / kPreBlock;
+    SURFEL_CUDA_OK(cudaMemsetAsync(p.scan_status, 0, (size_t)(blocks + 1) * 8, stream));
+    SURFEL_CUDA_OK(cudaMemsetAsync(p.counters, 0, 64, stream));
+    const bool vec4 = p.colors_precomp == nullptr && p.D == 3 && p.M == 16 &&
+                      (reinterpret_cast<uintptr_t>(p.shs) % 16 == 0);
+    if (vec4) preprocess_fwd_kernel<true><<<blocks, kPreBlock, 0, stream>>>(p);
+    else      preprocess_fwd_kernel<false><<<blocks, kPreBlock, 0, stream>>>(p);
+    SURFEL_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
+                        cudaStream_t stream) {
+    if (P <= 0) return 0;
+    mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, present);
+    SURFEL_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace surfel

@@ -1,0 +1,235 @@
+"""diff_surfel_rasterization — B200-native drop-in for the reference's rasterizer module.
+
+Same import name and public surface as the (un-vendored) upstream Python package
+hbb1/diff-surfel-rasterization that the reference imports at
+/root/reference/gaussian_renderer/__init__.py:14 and drives at :37-53 and :97-106:
+
+    GaussianRasterizationSettings   NamedTuple, 12 fields in the reference's order
+    GaussianRasterizer(nn.Module)   .forward(means3D, means2D, opacities, shs=None,
+                                             colors_precomp=None, scales=None, rotations=None,
+                                             cov3D_precomp=None) -> (color, radii, allmap)
+                                    .markVisible(positions) -> bool (P,)
+    rasterize_gaussians(...)        functional form
+
+Return order and `allmap` channel layout follow SURVEY.md §8(b) / the consumer at
+/root/reference/gaussian_renderer/__init__.py:110-135: color (3,H,W), radii (P,) int32,
+allmap (7,H,W) = [sum w*depth, alpha, normal xyz (view space), median depth, distortion].
+`means2D.grad` receives the densification proxy, as train.py:127-128 expects.
+
+All compute happens in libsurfel_b200.so (hand-written sm_100a CUDA behind the C ABI in
+include/surfel_rasterizer.h) on the current PyTorch CUDA stream.  PyTorch is only used for
+device memory, streams and autograd plumbing.  There is NO fallback path: a missing library or a
+CPU tensor raises.
+"""
+import ctypes
+import os
+from typing import NamedTuple, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _cabi
+
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians"]
+
+# Recalled upstream behaviour in the low-pass branch of the render backward that is NOT the
+# derivative of the forward (adds s.x*dL_dz, s.y*dL_dz to dL_dTw.xy).  Off by default; see DESIGN.md.
+LOWPASS_DEPTH_QUIRK = bool(int(os.environ.get("SURFEL_LOWPASS_DEPTH_QUIRK", "0")))
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+    # extension (keyword-only in practice): tile-row band [begin, end) for the multi-GPU tile-band
+    # partition; None = whole frame.
+    tile_rows: Optional[Tuple[int, int]] = None
+
+
+def _dev_f32(t, name, align=4):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError(f"diff_surfel_rasterization: `{name}` must be a CUDA tensor (no CPU path)")
+    if t.dtype != torch.float32:
+        t = t.float()
+    t = t.contiguous()
+    if t.data_ptr() % align:
+        t = t.clone()
+    return t
+
+
+def _ptr(t):
+    return None if t is None or t.numel() == 0 else t.data_ptr()
+
+
+def _settings_struct(rs: GaussianRasterizationSettings, keep):
+    bg = _dev_f32(rs.bg, "bg")
+    vm = _dev_f32(rs.viewmatrix, "viewmatrix")
+    pm = _dev_f32(rs.projmatrix, "projmatrix")
+    cp = _dev_f32(rs.campos, "campos")
+    keep.extend([bg, vm, pm, cp])
+    rows = rs.tile_rows if len(rs) > 12 and rs.tile_rows is not None else (0, 0)
+    return _cabi.SurfelSettings(
+        int(rs.image_height), int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy),
+        float(rs.scale_modifier), int(rs.sh_degree), int(bool(rs.prefiltered)), int(bool(rs.debug)),
+        int(rows[0]), int(rows[1]), bg.data_ptr(), vm.data_ptr(), pm.data_ptr(), cp.data_ptr())
+
+
+_pinned_counter = {}
+
+
+def _pinned_u32(device):
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    buf = _pinned_counter.get(key)
+    if buf is None:
+        buf = torch.zeros(1, dtype=torch.int32).pin_memory()
+        _pinned_counter[key] = buf
+    return buf
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    """Autograd node around the C ABI (upstream: _RasterizeGaussians)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                cov3Ds_precomp, raster_settings):
+        lib = _cabi.load()
+        rs = raster_settings
+        if means3D.dim() != 2 or means3D.shape[1] != 3:
+            raise RuntimeError("means3D must have dimensions (num_points, 3)")
+        P = means3D.shape[0]
+        dev = means3D.device
+        H, W = int(rs.image_height), int(rs.image_width)
+        keep = []
+        cs = _settings_struct(rs, keep)
+        means3D = _dev_f32(means3D, "means3D")
+        opacities = _dev_f32(opacities, "opacities")
+        sh = _dev_f32(sh, "shs", 16) if sh is not None and sh.numel() else None
+        colors_precomp = _dev_f32(colors_precomp, "colors_precomp") if colors_precomp is not None and colors_precomp.numel() else None
+        scales = _dev_f32(scales, "scales", 8) if scales is not None and scales.numel() else None
+        rotations = _dev_f32(rotations, "rotations", 16) if rotations is not None and rotations.numel() else None
+        cov3Ds_precomp = _dev_f32(cov3Ds_precomp, "cov3D_precomp") if cov3Ds_precomp is not None and cov3Ds_precomp.numel() else None
+        M = 0 if sh is None else sh.shape[1]
+
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        band = cs.tile_row_begin != 0 or cs.tile_row_end != 0
+        alloc = torch.zeros if band else torch.empty
+        color = alloc((3, H, W), dtype=torch.float32, device=dev)
+        allmap = alloc((7, H, W), dtype=torch.float32, device=dev)
+        radii = torch.empty((P,), dtype=torch.int32, device=dev)
+        geom = torch.empty((lib.surfel_geom_bytes(P),), dtype=torch.uint8, device=dev)
+        img = torch.empty((lib.surfel_image_bytes(W, H),), dtype=torch.uint8, device=dev)
+        R = 0
+        with torch.cuda.device(dev):
+            if P > 0:
+                host_R = _pinned_u32(dev)
+                _cabi.check(lib.surfel_forward_preprocess(
+                    ctypes.byref(cs), P, M, _ptr(means3D), _ptr(opacities), _ptr(scales),
+                    _ptr(rotations), _ptr(cov3Ds_precomp), _ptr(sh), _ptr(colors_precomp),
+                    radii.data_ptr(), geom.data_ptr(), host_R.data_ptr(), stream))
+                # the one host<->device sync of the forward: R sizes the binning workspace
+                torch.cuda.current_stream(dev).synchronize()
+                R = int(host_R.item()) & 0xFFFFFFFF
+            binning = torch.empty((lib.surfel_binning_bytes(R, W, H),), dtype=torch.uint8, device=dev)
+            _cabi.check(lib.surfel_forward_render(
+                ctypes.byref(cs), P, R, radii.data_ptr(), geom.data_ptr(), binning.data_ptr(),
+                img.data_ptr(), color.data_ptr(), allmap.data_ptr(), stream))
+
+        ctx.raster_settings = rs
+        ctx.num_rendered = R
+        ctx.M = M
+        ctx.flags = (sh is not None, colors_precomp is not None, scales is not None, cov3Ds_precomp is not None)
+        none = torch.empty(0, device=dev)
+        ctx.save_for_backward(means3D, none if scales is None else scales,
+                              none if rotations is None else rotations,
+                              none if cov3Ds_precomp is None else cov3Ds_precomp,
+                              none if sh is None else sh, radii, geom, binning, img)
+        ctx.mark_non_differentiable(radii)
+        return color, radii, allmap
+
+    @staticmethod
+    def backward(ctx, grad_color, grad_radii, grad_allmap):
+        lib = _cabi.load()
+        rs = ctx.raster_settings
+        means3D, scales, rotations, cov3Ds, sh, radii, geom, binning, img = ctx.saved_tensors
+        has_sh, has_colors, has_scales, has_cov = ctx.flags
+        P, M, R = means3D.shape[0], ctx.M, ctx.num_rendered
+        dev = means3D.device
+        H, W = int(rs.image_height), int(rs.image_width)
+        keep = []
+        cs = _settings_struct(rs, keep)
+        g_color = _dev_f32(grad_color if grad_color is not None else torch.zeros((3, H, W), device=dev), "grad_color")
+        g_all = _dev_f32(grad_allmap if grad_allmap is not None else torch.zeros((7, H, W), device=dev), "grad_allmap")
+
+        def e(*shape):
+            return torch.empty(shape, dtype=torch.float32, device=dev)
+        d_means2D, d_opacity, d_means3D = e(P, 3), e(P, 1), e(P, 3)
+        d_colors = e(P, 3) if has_colors else None
+        d_cov = e(P, 9) if has_cov else None
+        d_sh = e(P, M, 3) if has_sh else None
+        d_scales = e(P, 2) if has_scales else None
+        d_rot = e(P, 4) if has_scales else None
+        scratch = e(max(P, 1), 20)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            _cabi.check(lib.surfel_backward(
+                ctypes.byref(cs), P, M, R, _ptr(means3D), _ptr(scales), _ptr(rotations), _ptr(cov3Ds),
+                _ptr(sh), int(has_colors), radii.data_ptr(), geom.data_ptr(), binning.data_ptr(),
+                img.data_ptr(), g_color.data_ptr(), g_all.data_ptr(), scratch.data_ptr(),
+                d_means2D.data_ptr(), _ptr(d_colors), d_opacity.data_ptr(), d_means3D.data_ptr(),
+                _ptr(d_cov), _ptr(d_sh), _ptr(d_scales), _ptr(d_rot), int(LOWPASS_DEPTH_QUIRK), stream))
+        # (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, settings)
+        return d_means3D, d_means2D, d_sh, d_colors, d_opacity, d_scales, d_rot, d_cov, None
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                        cov3Ds_precomp, raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales,
+                                     rotations, cov3Ds_precomp, raster_settings)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        """Near-plane visibility of (P,3) positions -> bool (P,) (upstream mark_visible)."""
+        lib = _cabi.load()
+        rs = self.raster_settings
+        with torch.no_grad():
+            pos = _dev_f32(positions, "positions")
+            vm = _dev_f32(rs.viewmatrix, "viewmatrix")
+            pm = _dev_f32(rs.projmatrix, "projmatrix")
+            out = torch.empty((pos.shape[0],), dtype=torch.uint8, device=pos.device)
+            with torch.cuda.device(pos.device):
+                _cabi.check(lib.surfel_mark_visible(pos.shape[0], _ptr(pos), vm.data_ptr(), pm.data_ptr(),
+                                                    _ptr(out), torch.cuda.current_stream(pos.device).cuda_stream))
+        return out.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None,
+                rotations=None, cov3D_precomp=None):
+        rs = self.raster_settings
+        if (shs is None) == (colors_precomp is None):
+            raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+        geometric = scales is not None or rotations is not None
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or (geometric and cov3D_precomp is not None):
+            raise Exception("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!")
+        empty = torch.Tensor([])
+        shs = empty if shs is None else shs
+        colors_precomp = empty if colors_precomp is None else colors_precomp
+        scales = empty if scales is None else scales
+        rotations = empty if rotations is None else rotations
+        cov3D_precomp = empty if cov3D_precomp is None else cov3D_precomp
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales,
+                                   rotations, cov3D_precomp, rs)

@@ -42,12 +42,18 @@ def projection_matrix(znear, zfar, fovX, fovY):
     return P
 
 
-def world2view(R, t):
-    """W2C with R stored transposed, COLMAP convention (reference utils/graphics_utils.py:38-49)."""
+def world2view(R, t, translate=np.array([0.0, 0.0, 0.0]), scale=1.0):
+    """W2C with R stored transposed, COLMAP convention, including the reference's inverse /
+    re-inverse round trip so the float32 result is bit-identical
+    (reference utils/graphics_utils.py:38-49, getWorld2View2)."""
     Rt = np.zeros((4, 4))
     Rt[:3, :3] = R.transpose()
     Rt[:3, 3] = t
     Rt[3, 3] = 1.0
+    C2W = np.linalg.inv(Rt)
+    cam_center = (C2W[:3, 3] + translate) * scale
+    C2W[:3, 3] = cam_center
+    Rt = np.linalg.inv(C2W)
     return np.float32(Rt)
 
 

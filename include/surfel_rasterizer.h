@@ -1,0 +1,140 @@
+/*
+ * surfel_rasterizer.h — C ABI of the B200-native differentiable 2D-surfel rasterizer
+ * (libsurfel_b200.so, built from 2d-gaussian-splatting_b200/csrc by nvcc for sm_100a).
+ *
+ * This is the drop-in boundary for the native module of hbb1/diff-surfel-rasterization
+ * (pinned by /root/reference/.SUBMODULES.json:10-14; its C++/CUDA sources are NOT vendored in
+ * /root/reference, so the citations below are to the reference's own call sites and to
+ * SURVEY.md §8(b), which records the upstream pybind11 signatures being replaced):
+ *
+ *   upstream _C.rasterize_gaussians(bg, means3D, colors, opacity, scales, rotations,
+ *       scale_modifier, transMat_precomp, viewmatrix, projmatrix, tan_fovx, tan_fovy, H, W, sh,
+ *       degree, campos, prefiltered, debug) -> (num_rendered, color, others, radii, geomBuffer,
+ *       binningBuffer, imgBuffer)
+ *     == surfel_forward_preprocess()  [preprocess + tile-count scan -> num_rendered]
+ *      + surfel_forward_render()      [duplicateWithKeys, radix sort, tile ranges, blend]
+ *     reference call site: /root/reference/gaussian_renderer/__init__.py:37-53, :97-106
+ *   upstream _C.rasterize_gaussians_backward(...) -> 8 gradient tensors
+ *     == surfel_backward()
+ *     reference consumers: /root/reference/train.py:90, :127-128,
+ *                          /root/reference/scene/gaussian_model.py:405-407
+ *   upstream _C.mark_visible(means3D, viewmatrix, projmatrix) -> bool tensor
+ *     == surfel_mark_visible()
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - all tensors are contiguous float32 unless stated; "absent" optional inputs are NULL
+ *     (upstream passes empty tensors);
+ *   - ownership: the caller (PyTorch on the Python side) owns every buffer, including the three
+ *     opaque workspaces (geometry / binning / image state) whose sizes the *_bytes() functions
+ *     return; forward fills them, backward reads them, nothing is retained across calls;
+ *   - every launch is ordered on the cudaStream_t passed as `stream` (void*); no call synchronises
+ *     the device; the library holds no global mutable state besides the last-error string;
+ *   - return value: 0 on success, non-zero on failure with surfel_last_error() describing it
+ *     (the Python wrapper raises RuntimeError, like upstream's AT_ERROR path).
+ */
+#ifndef SURFEL_RASTERIZER_H_
+#define SURFEL_RASTERIZER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SURFEL_ABI_VERSION 1
+
+/* Mirrors GaussianRasterizationSettings (fields constructed at
+ * /root/reference/gaussian_renderer/__init__.py:37-51) plus the tile-row band used by the
+ * multi-GPU tile-band partition.  tile_row_begin == tile_row_end == 0 => full frame. */
+typedef struct surfel_settings {
+    int32_t image_height;
+    int32_t image_width;
+    float tanfovx;
+    float tanfovy;
+    float scale_modifier;
+    int32_t sh_degree;
+    int32_t prefiltered;
+    int32_t debug;
+    int32_t tile_row_begin;
+    int32_t tile_row_end;
+    const float* bg;          /* (3)    device */
+    const float* viewmatrix;  /* (4,4)  device, row-vector convention (scene/cameras.py:56) */
+    const float* projmatrix;  /* (4,4)  device, viewmatrix @ P^T      (scene/cameras.py:57-58) */
+    const float* campos;      /* (3)    device                        (scene/cameras.py:59) */
+} surfel_settings_t;
+
+int surfel_abi_version(void);
+const char* surfel_last_error(void);
+
+/* Workspace sizes (bytes).  R = number of (splat, tile) instances ("num_rendered"). */
+size_t surfel_geom_bytes(int P);
+size_t surfel_image_bytes(int W, int H);
+size_t surfel_binning_bytes(size_t R, int W, int H);
+
+/* Byte offsets of the sub-arrays inside the workspaces, for tests and debugging.
+ *   geom   : out[0]=splat records (P x 96 B), [1]=tiles_touched u32, [2]=offsets u32 (inclusive),
+ *            [3]=clamped u8 (bit c = channel c clamped), [4]=counters u32 ([1] = R)
+ *   binning: out[0]=keys_unsorted u64, [1]=vals_unsorted u32, [2]=keys_sorted u64,
+ *            [3]=vals_sorted u32 (the per-tile point list), [4]=ranges uint2 per tile
+ *            (unsorted and sorted regions coincide when the sort runs an even number of passes)
+ *   image  : out[0]=accum f32 (final_T, M1, M2 planes), [1]=n_contrib u32 (last, median planes) */
+int surfel_geom_offsets(int P, size_t* out5);
+int surfel_binning_offsets(size_t R, int W, int H, size_t* out5);
+int surfel_image_offsets(int W, int H, size_t* out2);
+
+/* Forward, stage 1: preprocess every splat and scan tiles_touched.  Writes radii (P) int32 and the
+ * geometry workspace.  The instance count R is left in the workspace and, if
+ * num_rendered_host != NULL (pinned host memory), copied there asynchronously on `stream`; the
+ * caller synchronises the stream (or an event) before reading it to size the binning workspace. */
+int surfel_forward_preprocess(const surfel_settings_t* s, int P, int M, const float* means3D,
+                              const float* opacities, const float* scales, const float* rotations,
+                              const float* transMat_precomp, const float* shs,
+                              const float* colors_precomp, int32_t* radii, void* geom_ws,
+                              uint32_t* num_rendered_host, void* stream);
+
+/* Forward, stage 2: emit keys, sort, find tile ranges, blend.  out_color (3,H,W), out_others
+ * (7,H,W): 0 = sum w*depth, 1 = alpha, 2-4 = view-space normal, 5 = median depth, 6 = distortion
+ * (channel order consumed at /root/reference/gaussian_renderer/__init__.py:118-135). */
+int surfel_forward_render(const surfel_settings_t* s, int P, uint32_t R, const int32_t* radii,
+                          const void* geom_ws, void* binning_ws, void* image_ws, float* out_color,
+                          float* out_others, void* stream);
+
+/* The two halves of stage 2, exposed separately for parity tests. */
+int surfel_bin_duplicate(const surfel_settings_t* s, int P, uint32_t R, const void* geom_ws,
+                         const int32_t* radii, void* binning_ws, void* stream);
+int surfel_bin_sort(const surfel_settings_t* s, uint32_t R, void* binning_ws, void* stream);
+int surfel_render_forward(const surfel_settings_t* s, uint32_t R, const void* geom_ws,
+                          const void* binning_ws, void* image_ws, float* out_color,
+                          float* out_others, void* stream);
+
+/* Backward.  dL_dout_color (3,H,W), dL_dout_others (7,H,W).  grad_scratch: P*20 floats (zeroed
+ * here).  Outputs are written for every splat (zeros where culled), so they may be uninitialised:
+ *   dL_dmeans2D (P,3) [densification proxy in .xy, SURVEY A.5], dL_dcolors (P,3),
+ *   dL_dopacity (P,1), dL_dmeans3D (P,3), dL_dtransMat (P,9), dL_dsh (P,M,3),
+ *   dL_dscales (P,2), dL_drotations (P,4).  Optional outputs may be NULL when the matching input
+ *   is absent.  lowpass_depth_quirk: see DESIGN.md (default 0). */
+int surfel_backward(const surfel_settings_t* s, int P, int M, uint32_t R, const float* means3D,
+                    const float* scales, const float* rotations, const float* transMat_precomp,
+                    const float* shs, int has_colors_precomp, const int32_t* radii,
+                    const void* geom_ws, const void* binning_ws, const void* image_ws,
+                    const float* dL_dout_color, const float* dL_dout_others, float* grad_scratch,
+                    float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D,
+                    float* dL_dtransMat, float* dL_dsh, float* dL_dscales, float* dL_drotations,
+                    int lowpass_depth_quirk, void* stream);
+
+/* GaussianRasterizer.markVisible: near-plane test (present: P bytes, 0/1). */
+int surfel_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                        const float* projmatrix, uint8_t* present, void* stream);
+
+/* Stand-alone CUB-free stable radix sort of (u64 key, u32 value) pairs on key bits [0,end_bit).
+ * Data starts in A; *result_in_b tells where the sorted pairs are (buffers ping-pong per pass). */
+size_t surfel_sort_temp_bytes(size_t n);
+int surfel_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
+                      size_t n, int end_bit, void* temp, int* result_in_b, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SURFEL_RASTERIZER_H_ */
