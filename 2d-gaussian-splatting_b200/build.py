@@ -18,6 +18,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 SOURCES = {
     "api.cu": [],
+    "profile.cu": [],
     "preprocess_fwd.cu": ["-fmad=false"],
     "preprocess_bwd.cu": [],
     "binning.cu": [],

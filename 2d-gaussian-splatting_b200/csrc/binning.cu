@@ -11,6 +11,7 @@
 // thousands of tiles is spread over the whole block.
 #include "common.cuh"
 #include "kernels.h"
+#include "profile.h"
 
 namespace surfel {
 
@@ -79,6 +80,7 @@ int launch_duplicate_with_keys(int P, int gx, int gy, int row0, int row1, const 
                                const int* radii, const uint32_t* offsets, uint64_t* keys,
                                uint32_t* vals, cudaStream_t stream) {
     if (P <= 0) return 0;
+    LaunchScope scope(kStDuplicate, stream);
     duplicate_with_keys_kernel<<<(P + kDupBlock - 1) / kDupBlock, kDupBlock, 0, stream>>>(
         P, gx, gy, row0, row1, rec, radii, offsets, keys, vals);
     SURFEL_CUDA_OK(cudaGetLastError());
@@ -89,6 +91,7 @@ int launch_identify_tile_ranges(size_t R, int tiles, const uint64_t* keys_sorted
                                 cudaStream_t stream) {
     SURFEL_CUDA_OK(cudaMemsetAsync(ranges, 0, (size_t)tiles * sizeof(uint2), stream));
     if (R == 0) return 0;
+    LaunchScope scope(kStRanges, stream);
     identify_tile_ranges_kernel<<<(unsigned)((R + 255) / 256), 256, 0, stream>>>(R, keys_sorted, ranges);
     SURFEL_CUDA_OK(cudaGetLastError());
     return 0;

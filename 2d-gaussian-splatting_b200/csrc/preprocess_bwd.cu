@@ -11,6 +11,7 @@
 // Kept quirk: dL_dscale ignores scale_modifier (only the viewer uses modifier != 1).
 #include "common.cuh"
 #include "kernels.h"
+#include "profile.h"
 
 namespace surfel {
 
@@ -192,6 +193,7 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(PreBwdParams p) {
 
 int launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t stream) {
     if (p.P <= 0) return 0;
+    LaunchScope scope(kStPreBwd, stream);
     preprocess_bwd_kernel<<<(p.P + 127) / 128, 128, 0, stream>>>(p);
     SURFEL_CUDA_OK(cudaGetLastError());
     return 0;

@@ -18,6 +18,7 @@
 // bit-identical to the CPU restatement.
 #include "common.cuh"
 #include "kernels.h"
+#include "profile.h"
 
 namespace surfel {
 
@@ -340,6 +341,7 @@ int launch_preprocess_fwd(const PreFwdParams& p, cudaStream_t stream) {
     SURFEL_CUDA_OK(cudaMemsetAsync(p.counters, 0, 64, stream));
     const bool vec4 = p.colors_precomp == nullptr && p.D == 3 && p.M == 16 &&
                       (reinterpret_cast<uintptr_t>(p.shs) % 16 == 0);
+    LaunchScope scope(kStPreFwd, stream);
     if (vec4) preprocess_fwd_kernel<true><<<blocks, kPreBlock, 0, stream>>>(p);
     else      preprocess_fwd_kernel<false><<<blocks, kPreBlock, 0, stream>>>(p);
     SURFEL_CUDA_OK(cudaGetLastError());
@@ -349,6 +351,7 @@ int launch_preprocess_fwd(const PreFwdParams& p, cudaStream_t stream) {
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
                         cudaStream_t stream) {
     if (P <= 0) return 0;
+    LaunchScope scope(kStMarkVisible, stream);
     mark_visible_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, means3D, viewmatrix, present);
     SURFEL_CUDA_OK(cudaGetLastError());
     return 0;

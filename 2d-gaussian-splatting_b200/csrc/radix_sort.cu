@@ -14,6 +14,7 @@
 #include <utility>
 #include "common.cuh"
 #include "kernels.h"
+#include "profile.h"
 
 namespace surfel {
 
@@ -257,9 +258,11 @@ int launch_radix_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b
         attr_set = true;
     }
     const int hist_blocks = (int)std::min((size_t)148 * 8, (n + 255) / 256);
+    { LaunchScope scope(kStSortHist, stream);
     radix_histogram_kernel<<<hist_blocks, 256, 0, stream>>>(keys_a, n, passes, end_bit, t.hist);
     SURFEL_CUDA_OK(cudaGetLastError());
-    radix_scan_hist_kernel<<<passes, kRadix, 0, stream>>>(t.hist);
+    prof_count_launch();
+    radix_scan_hist_kernel<<<passes, kRadix, 0, stream>>>(t.hist); }
     SURFEL_CUDA_OK(cudaGetLastError());
 
     // ping-pong A -> B -> A ...: the result is in B after an odd number of passes, else in A
@@ -269,6 +272,7 @@ int launch_radix_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b
     for (int ps = 0; ps < passes; ps++) {
         const int shift = ps * kRadixBits;
         const uint32_t mask = (1u << std::min(kRadixBits, end_bit - shift)) - 1u;
+        LaunchScope scope(kStSortPass, stream);
         radix_onesweep_kernel<<<(unsigned)tiles, kSortThreads, sizeof(SortSmem), stream>>>(
             ka, va, kb, vb, n, shift, mask, t.hist + ps * kRadix, t.tickets + ps,
             t.status + (size_t)ps * tiles * kRadix);

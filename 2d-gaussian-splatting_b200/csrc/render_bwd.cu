@@ -9,64 +9,25 @@
 // B200 design (not upstream's, which issues up to 16 global float atomics per (pixel,splat)):
 //  * same 96-byte records / 8x4 warp footprints / bbox ballot culling as the forward (exact);
 //  * the CTA starts at the largest last_contributor of its pixels, not at the end of the list;
-//  * the 18 per-pair partials are reduced ACROSS THE WARP first: a 16-value halving butterfly
-//    (16 shuffles) + 2 plain xor-reductions, after which 18 lanes issue one RED each into the
-//    splat's 80-byte gradient record — 18 contiguous atomics per (warp,splat) instead of 18 per
-//    (pixel,splat), and none at all when no lane of the warp got a contribution.
+//  * per (warp, splat) the lanes that really contribute (on average ~9 of 32 at 1 M splats / 1080p,
+//    ncu profiles/r1) are compacted with a ballot: each writes its 18 partials as one 80-byte row
+//    into a per-warp shared-memory panel, then 18 lanes each add one COLUMN of the panel and issue
+//    ONE red.global.add.f32 into the splat's 80-byte gradient record.  Work scales with the number
+//    of contributing lanes (a 32-lane shuffle butterfly cost 108 instructions per splat regardless),
+//    and global atomics drop from 18 per (pixel,splat) to 18 per (warp,splat), contiguous.
 #include "render_common.cuh"
 #include "kernels.h"
+#include "profile.h"
 
 namespace surfel {
 
 constexpr int kBatchB = 256;
+constexpr int kPanelRow = kGradFloats;            // 20 floats = 80 B per contributing lane
 
-// Sum v[0..15] over the 32 lanes; on return lane L holds the total of value index (L >> 1) in v[0].
-__device__ __forceinline__ void warp_reduce16(float (&v)[16], int lane) {
-    {
-        const bool up = lane & 16;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const float send = up ? v[j] : v[j + 8];
-            const float keep = up ? v[j + 8] : v[j];
-            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-    }
-    {
-        const bool up = lane & 8;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const float send = up ? v[j] : v[j + 4];
-            const float keep = up ? v[j + 4] : v[j];
-            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-    }
-    {
-        const bool up = lane & 4;
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-            const float send = up ? v[j] : v[j + 2];
-            const float keep = up ? v[j + 2] : v[j];
-            v[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-    }
-    {
-        const bool up = lane & 2;
-        const float send = up ? v[0] : v[1];
-        const float keep = up ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-
-__device__ __forceinline__ float warp_sum(float x) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
-    return x;
-}
-
-__global__ void __launch_bounds__(256, 2) render_bwd_kernel(RenderParams p) {
-    __shared__ float4 s_rec[kRecQuads * kBatchB];   // [quad][slot]
+__global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderParams p) {
+    __shared__ float4 s_rec[kRecQuads * kBatchB];            // [quad][slot]
     __shared__ uint32_t s_id[kBatchB];
+    __shared__ __align__(16) float s_panel[8 * 32 * kPanelRow];
     __shared__ uint32_t s_max[8];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -81,6 +42,9 @@ __global__ void __launch_bounds__(256, 2) render_bwd_kernel(RenderParams p) {
     const uint2 range = p.ranges[ty * p.gx + tx];
     const size_t HW = (size_t)p.H * p.W;
     const size_t pix = (size_t)py * p.W + px;
+    const uint32_t rec_base = smem_u32(s_rec);
+    const uint32_t panel_base = smem_u32(s_panel) + warp * (32 * kPanelRow * 4);
+    const unsigned lt_mask = (1u << lane) - 1u;
 
     float T_final = 0, final_D = 0, final_D2 = 0;
     uint32_t last_contributor = 0, median_contributor = 0;
@@ -99,7 +63,8 @@ __global__ void __launch_bounds__(256, 2) render_bwd_kernel(RenderParams p) {
         dL_dreg = p.dL_dothers[kChDistortion * HW + pix];
     }
     const float final_A = 1.0f - T_final;
-    const float bg_dot = (__ldg(p.bg + 0) * dpix0 + __ldg(p.bg + 1) * dpix1) + __ldg(p.bg + 2) * dpix2;
+    const float bgT = -T_final * ((__ldg(p.bg + 0) * dpix0 + __ldg(p.bg + 1) * dpix1) + __ldg(p.bg + 2) * dpix2);
+    const uint32_t median_index = median_contributor - 1u;   // 0xFFFFFFFE when there is none
 
     // warp / CTA extent of the replay
     uint32_t warp_max = last_contributor;
@@ -115,6 +80,8 @@ __global__ void __launch_bounds__(256, 2) render_bwd_kernel(RenderParams p) {
     float last_c0 = 0, last_c1 = 0, last_c2 = 0, acc_c0 = 0, acc_c1 = 0, acc_c2 = 0;
     float last_depth = 0, acc_depth = 0, acc_alpha = 0;
     float last_n0 = 0, last_n1 = 0, last_n2 = 0, acc_n0 = 0, acc_n1 = 0, acc_n2 = 0;
+    constexpr float kMScale = kFar / (kFar - kNear);
+    constexpr float kDmScale = (kFar * kNear) / (kFar - kNear);
 
     for (int end = (int)cta_max; end > 0; end -= kBatchB) {
         const int n = min(kBatchB, end);
@@ -134,7 +101,7 @@ __global__ void __launch_bounds__(256, 2) render_bwd_kernel(RenderParams p) {
             const int slot = c + lane;
             bool hit = false;
             if (slot < n && (uint32_t)(start + slot) < warp_max) {
-                const float4 bb = s_rec[5 * kBatchB + slot];
+                const float4 bb = lds128(rec_base + (5 * kBatchB + slot) * 16);
                 hit = bb.x <= fx1 && bb.z >= fx0 && bb.y <= fy1 && bb.w >= fy0;
             }
             unsigned m = __ballot_sync(0xffffffffu, hit);
@@ -143,86 +110,89 @@ __global__ void __launch_bounds__(256, 2) render_bwd_kernel(RenderParams p) {
                 m &= ~(1u << j);
                 const int k = c + j;
                 const uint32_t index = (uint32_t)(start + k);   // 0-based contributor
-                const float4 q0 = s_rec[0 * kBatchB + k], q1 = s_rec[1 * kBatchB + k], q2 = s_rec[2 * kBatchB + k];
+                const uint32_t ra = rec_base + k * 16;
+                const float4 q0 = lds128(ra), q1 = lds128(ra + kBatchB * 16), q2 = lds128(ra + 2 * kBatchB * 16);
                 PairEval e;
                 const bool active = index < last_contributor && eval_pair(pxf, pyf, q0, q1, q2, e);
-                if (!__any_sync(0xffffffffu, active)) continue;
+                const unsigned am = __ballot_sync(0xffffffffu, active);
+                if (am == 0u) continue;
 
-                float g[16];
-#pragma unroll
-                for (int i = 0; i < 16; i++) g[i] = 0.0f;
-                float gc1 = 0.0f, gc2 = 0.0f;
                 if (active) {
-                    const float4 q3 = s_rec[3 * kBatchB + k], q4 = s_rec[4 * kBatchB + k];
+                    const float4 q3 = lds128(ra + 3 * kBatchB * 16), q4 = lds128(ra + 4 * kBatchB * 16);
                     const float G = e.G, alpha = e.alpha;
-                    T = T / (1.0f - alpha);
+                    const float one_m = 1.0f - alpha;
+                    const float inv1ma = fast_rcp(one_m);
+                    T = T * inv1ma;
                     const float w = alpha * T;
-                    float dL_dalpha = 0.0f;
+                    const float la = last_alpha, ola = 1.0f - last_alpha;
                     // colour
-                    acc_c0 = last_alpha * last_c0 + (1.0f - last_alpha) * acc_c0; last_c0 = q4.x;
-                    acc_c1 = last_alpha * last_c1 + (1.0f - last_alpha) * acc_c1; last_c1 = q4.y;
-                    acc_c2 = last_alpha * last_c2 + (1.0f - last_alpha) * acc_c2; last_c2 = q4.z;
-                    dL_dalpha += (q4.x - acc_c0) * dpix0 + (q4.y - acc_c1) * dpix1 + (q4.z - acc_c2) * dpix2;
-                    g[15] = w * dpix0; gc1 = w * dpix1; gc2 = w * dpix2;
+                    acc_c0 = la * last_c0 + ola * acc_c0; last_c0 = q4.x;
+                    acc_c1 = la * last_c1 + ola * acc_c1; last_c1 = q4.y;
+                    acc_c2 = la * last_c2 + ola * acc_c2; last_c2 = q4.z;
+                    float dL_dalpha = (q4.x - acc_c0) * dpix0 + (q4.y - acc_c1) * dpix1 + (q4.z - acc_c2) * dpix2;
                     // distortion + median depth
-                    float dL_dz = 0.0f;
-                    const float m_d = kFar / (kFar - kNear) * (1.0f - kNear / e.depth);
-                    const float dmd_dd = (kFar * kNear) / ((kFar - kNear) * e.depth * e.depth);
-                    if (index == median_contributor - 1u) dL_dz += dL_dmedian;
+                    const float inv_d = fast_rcp(e.depth);
+                    const float m_d = kMScale * (1.0f - kNear * inv_d);
+                    const float dmd_dd = kDmScale * inv_d * inv_d;
+                    float dL_dz = (index == median_index) ? dL_dmedian : 0.0f;
                     const float dL_dweight = (final_D2 + m_d * m_d * final_A - 2.0f * m_d * final_D) * dL_dreg;
                     dL_dalpha += dL_dweight - last_dL_dT;
-                    last_dL_dT = dL_dweight * alpha + (1.0f - alpha) * last_dL_dT;
+                    last_dL_dT = dL_dweight * alpha + one_m * last_dL_dT;
                     dL_dz += 2.0f * w * (m_d * final_A - final_D) * dL_dreg * dmd_dd;
                     // expected depth, alpha
-                    acc_depth = last_alpha * last_depth + (1.0f - last_alpha) * acc_depth; last_depth = e.depth;
+                    acc_depth = la * last_depth + ola * acc_depth; last_depth = e.depth;
                     dL_dalpha += (e.depth - acc_depth) * dL_ddepth;
-                    acc_alpha = last_alpha + (1.0f - last_alpha) * acc_alpha;
+                    acc_alpha = la + ola * acc_alpha;
                     dL_dalpha += (1.0f - acc_alpha) * dL_daccum;
                     // normal
-                    acc_n0 = last_alpha * last_n0 + (1.0f - last_alpha) * acc_n0; last_n0 = q3.x;
-                    acc_n1 = last_alpha * last_n1 + (1.0f - last_alpha) * acc_n1; last_n1 = q3.y;
-                    acc_n2 = last_alpha * last_n2 + (1.0f - last_alpha) * acc_n2; last_n2 = q3.z;
+                    acc_n0 = la * last_n0 + ola * acc_n0; last_n0 = q3.x;
+                    acc_n1 = la * last_n1 + ola * acc_n1; last_n1 = q3.y;
+                    acc_n2 = la * last_n2 + ola * acc_n2; last_n2 = q3.z;
                     dL_dalpha += (q3.x - acc_n0) * dN0 + (q3.y - acc_n1) * dN1 + (q3.z - acc_n2) * dN2;
-                    g[12] = w * dN0; g[13] = w * dN1; g[14] = w * dN2;
 
                     dL_dalpha *= T;
                     last_alpha = alpha;
-                    dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot;
+                    dL_dalpha += bgT * inv1ma;
                     const float dL_dG = q2.w * dL_dalpha;
                     dL_dz += w * dL_ddepth;
+                    float g0 = 0, g1 = 0, g2 = 0, g3 = 0, g4 = 0, g5 = 0, g6 = 0, g7 = 0, g8, g9 = 0, g10 = 0;
                     if (e.use3d) {
                         const float Twx = q1.z, Twy = q1.w;
-                        const float dsx = dL_dG * -G * e.sx + dL_dz * Twx;
-                        const float dsy = dL_dG * -G * e.sy + dL_dz * Twy;
-                        const float inv = fast_rcp(e.pz);
-                        const float dpx = dsx * inv, dpy = dsy * inv;
+                        const float nG = -G * dL_dG;
+                        const float dsx = nG * e.sx + dL_dz * Twx;
+                        const float dsy = nG * e.sy + dL_dz * Twy;
+                        const float dpx = dsx * e.inv_pz, dpy = dsy * e.inv_pz;
                         const float dpz = -(dpx * e.sx + dpy * e.sy);
                         const float dkx = e.ly * dpz - e.lz * dpy, dky = e.lz * dpx - e.lx * dpz, dkz = e.lx * dpy - e.ly * dpx;
                         const float dlx = dpy * e.kz - dpz * e.ky, dly = dpz * e.kx - dpx * e.kz, dlz = dpx * e.ky - dpy * e.kx;
-                        g[0] = -dkx; g[1] = -dky; g[2] = -dkz;
-                        g[3] = -dlx; g[4] = -dly; g[5] = -dlz;
-                        g[6] = pxf * dkx + pyf * dlx + dL_dz * e.sx;
-                        g[7] = pxf * dky + pyf * dly + dL_dz * e.sy;
-                        g[8] = pxf * dkz + pyf * dlz + dL_dz;
+                        g0 = -dkx; g1 = -dky; g2 = -dkz;
+                        g3 = -dlx; g4 = -dly; g5 = -dlz;
+                        g6 = pxf * dkx + pyf * dlx + dL_dz * e.sx;
+                        g7 = pxf * dky + pyf * dly + dL_dz * e.sy;
+                        g8 = pxf * dkz + pyf * dlz + dL_dz;
                     } else {
                         const float gg = -G * kFilterInvSquare * dL_dG;
-                        g[9] = gg * e.dx; g[10] = gg * e.dy;
-                        if (p.lowpass_quirk) { g[6] = e.sx * dL_dz; g[7] = e.sy * dL_dz; }
-                        g[8] = dL_dz;
+                        g9 = gg * e.dx; g10 = gg * e.dy;
+                        if (p.lowpass_quirk) { g6 = e.sx * dL_dz; g7 = e.sy * dL_dz; }
+                        g8 = dL_dz;
                     }
-                    g[11] = G * dL_dalpha;
+                    // one 80-byte row per contributing lane (rows are compacted: ballot prefix)
+                    const uint32_t row = panel_base + __popc(am & lt_mask) * (kPanelRow * 4);
+                    sts128(row, make_float4(g0, g1, g2, g3));
+                    sts128(row + 16, make_float4(g4, g5, g6, g7));
+                    sts128(row + 32, make_float4(g8, g9, g10, G * dL_dalpha));
+                    sts128(row + 48, make_float4(w * dN0, w * dN1, w * dN2, w * dpix0));
+                    sts64(row + 64, w * dpix1, w * dpix2);
                 }
-                warp_reduce16(g, lane);
-                gc1 = warp_sum(gc1);
-                gc2 = warp_sum(gc2);
-                float* dst = p.grad_rec + (size_t)s_id[k] * kGradFloats;
-                if ((lane & 1) == 0) {
-                    if (g[0] != 0.0f) atomicAdd(dst + (lane >> 1), g[0]);
-                } else if (lane == 1) {
-                    if (gc1 != 0.0f) atomicAdd(dst + 16, gc1);
-                } else if (lane == 3) {
-                    if (gc2 != 0.0f) atomicAdd(dst + 17, gc2);
+                __syncwarp();
+                if (lane < 18) {
+                    const int nact = __popc(am);
+                    uint32_t a = panel_base + lane * 4;
+                    float acc = 0.0f;
+                    for (int r = 0; r < nact; r++, a += kPanelRow * 4) acc += lds32(a);
+                    if (acc != 0.0f) atomicAdd(p.grad_rec + (size_t)s_id[k] * kGradFloats + lane, acc);
                 }
+                __syncwarp();
             }
         }
     }
@@ -232,6 +202,7 @@ int launch_render_bwd(const RenderParams& p, cudaStream_t stream) {
     const int rows = p.row1 - p.row0;
     if (rows <= 0 || p.gx <= 0) return 0;
     dim3 grid(p.gx, rows);
+    LaunchScope scope(kStRenderBwd, stream);
     render_bwd_kernel<<<grid, 256, 0, stream>>>(p);
     SURFEL_CUDA_OK(cudaGetLastError());
     return 0;

@@ -11,7 +11,7 @@ namespace surfel {
 
 struct PairEval {
     float kx, ky, kz, lx, ly, lz;   // k = px*Tw - Tu, l = py*Tw - Tv
-    float pz;                       // cross(k,l).z
+    float pz, inv_pz;               // cross(k,l).z and its reciprocal
     float sx, sy;                   // splat-space intersection
     float dx, dy;                   // xy - pixel
     float depth, G, alpha;
@@ -41,6 +41,7 @@ __device__ __forceinline__ bool eval_pair(float pxf, float pyf, const float4& q0
     e.pz = __fmaf_rn(e.kx, e.ly, -__fmul_rn(e.ky, e.lx));
     if (e.pz == 0.0f) return false;
     const float inv = fast_rcp(e.pz);
+    e.inv_pz = inv;
     e.sx = __fmul_rn(ppx, inv); e.sy = __fmul_rn(ppy, inv);
     const float rho3d = __fmaf_rn(e.sx, e.sx, __fmul_rn(e.sy, e.sy));
     e.dx = __fsub_rn(q2.y, pxf); e.dy = __fsub_rn(q2.z, pyf);
@@ -55,6 +56,28 @@ __device__ __forceinline__ bool eval_pair(float pxf, float pyf, const float4& q0
     e.alpha = fminf(kAlphaMax, __fmul_rn(q2.w, e.G));
     if (e.alpha < kAlphaMin) return false;
     return true;
+}
+
+// Explicit shared-window addressing: one cvta per kernel instead of a generic->shared conversion
+// (S2UR CgaCtaId + ULEA) re-materialised in every inner-loop iteration.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts64(uint32_t addr, float a, float b) {
+    asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
 }
 
 // Warp footprint inside a 16x16 tile: 8 (x) by 4 (y) pixels; warp w sits at (w&1, w>>1).

@@ -15,6 +15,7 @@
 // Early termination is per warp (all 32 pixels done), then per CTA.
 #include "render_common.cuh"
 #include "kernels.h"
+#include "profile.h"
 
 namespace surfel {
 
@@ -36,6 +37,8 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderParams p) {
 
     const uint2 range = p.ranges[ty * p.gx + tx];
     const int total = (int)(range.y - range.x);
+    const uint32_t rec_base = smem_u32(s_rec);
+    constexpr float kMScale = kFar / (kFar - kNear);
 
     float T = 1.0f, C0 = 0, C1 = 0, C2 = 0, N0 = 0, N1 = 0, N2 = 0, D = 0, M1 = 0, M2 = 0, dist = 0;
     float median_depth = 0;
@@ -61,7 +64,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderParams p) {
                 const int slot = c + lane;
                 bool hit = false;
                 if (slot < n) {
-                    const float4 bb = s_rec[5 * kBatch + slot];
+                    const float4 bb = lds128(rec_base + (5 * kBatch + slot) * 16);
                     hit = bb.x <= fx1 && bb.z >= fx0 && bb.y <= fy1 && bb.w >= fy0;
                 }
                 unsigned m = __ballot_sync(0xffffffffu, hit);
@@ -70,7 +73,8 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderParams p) {
                     m &= m - 1;
                     const int k = c + j;
                     if (!done) {
-                        const float4 q0 = s_rec[0 * kBatch + k], q1 = s_rec[1 * kBatch + k], q2 = s_rec[2 * kBatch + k];
+                        const uint32_t ra = rec_base + k * 16;
+                        const float4 q0 = lds128(ra), q1 = lds128(ra + kBatch * 16), q2 = lds128(ra + 2 * kBatch * 16);
                         PairEval e;
                         if (eval_pair(pxf, pyf, q0, q1, q2, e)) {
                             const float test_T = T * (1.0f - e.alpha);
@@ -78,10 +82,10 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderParams p) {
                                 done = true;
                             } else {
                                 const uint32_t contributor = (uint32_t)(base + k + 1);
-                                const float4 q3 = s_rec[3 * kBatch + k], q4 = s_rec[4 * kBatch + k];
+                                const float4 q3 = lds128(ra + 3 * kBatch * 16), q4 = lds128(ra + 4 * kBatch * 16);
                                 const float w = e.alpha * T;
                                 const float A = 1.0f - T;
-                                const float mm = kFar / (kFar - kNear) * (1.0f - kNear / e.depth);
+                                const float mm = kMScale * (1.0f - kNear * fast_rcp(e.depth));
                                 dist += (mm * mm * A + M2 - 2.0f * mm * M1) * w;
                                 D += e.depth * w;
                                 M1 += mm * w;
@@ -122,6 +126,7 @@ int launch_render_fwd(const RenderParams& p, cudaStream_t stream) {
     const int rows = p.row1 - p.row0;
     if (rows <= 0 || p.gx <= 0) return 0;
     dim3 grid(p.gx, rows);
+    LaunchScope scope(kStRenderFwd, stream);
     render_fwd_kernel<<<grid, 256, 0, stream>>>(p);
     SURFEL_CUDA_OK(cudaGetLastError());
     return 0;

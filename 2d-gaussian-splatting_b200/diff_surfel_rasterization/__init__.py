@@ -86,6 +86,13 @@ def _settings_struct(rs: GaussianRasterizationSettings, keep):
 
 
 _pinned_counter = {}
+_last = {"num_rendered": 0}
+
+
+def last_num_rendered():
+    """Instance count R (splat-tile pairs) of the most recent forward in this process."""
+    return _last["num_rendered"]
+
 
 
 def _pinned_u32(device):
@@ -145,6 +152,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 ctypes.byref(cs), P, R, radii.data_ptr(), geom.data_ptr(), binning.data_ptr(),
                 img.data_ptr(), color.data_ptr(), allmap.data_ptr(), stream))
 
+        _last["num_rendered"] = R
         ctx.raster_settings = rs
         ctx.num_rendered = R
         ctx.M = M

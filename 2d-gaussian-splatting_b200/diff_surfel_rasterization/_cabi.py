@@ -44,6 +44,11 @@ SIGNATURES = {
                         + [c_void_p] * 15 + [c_int, c_void_p]),
     "surfel_mark_visible": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "surfel_sort_temp_bytes": (c_size_t, [c_size_t]),
+    "surfel_launch_count": (ctypes.c_ulonglong, []),
+    "surfel_profile_enable": (None, [c_int]),
+    "surfel_profile_num_stages": (c_int, []),
+    "surfel_profile_stage_name": (ctypes.c_char_p, [c_int]),
+    "surfel_profile_read": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_int)]),
     "surfel_sort_pairs": (c_int, [c_void_p] * 4 + [c_size_t, c_int, c_void_p, ctypes.POINTER(c_int), c_void_p]),
 }
 

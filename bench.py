@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py — fwd+bwd Msplats/s of the 2D-surfel rasterizer hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one forward + one backward of the op (diff_surfel_rasterization.GaussianRasterizer as
+/root/reference/gaussian_renderer/__init__.py:97-106 calls it, then autograd backward with dense
+cotangents on all 10 output channels) over one synthetic view (SURVEY §8(d) generator).
+Default workload = the configuration the metric is quoted on: 1 M surfels, 1920x1080, SH degree 3.
+N > 1: one process per GPU (torchrun), independent views sharded one per rank, no data-path
+collective ("scaling": "weak"); time = max over ranks.
+
+Prints ONE JSON line (see the task contract): value (inputs resident in HBM), e2e (host buffers,
+H2D of every input and D2H of outputs + gradients inside the timed region), roofline of the
+dominant kernel (timed live with CUDA events on the launching stream), cpu_baseline (the C oracle
+port on the host cores), clocks, gpu_launches.
+
+--impl reference: the reference's CUDA rasterizer is not vendored in /root/reference, so
+the reference arm is the CPU restatement (oracle/, "port") on the box's host cores, same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "2d-gaussian-splatting_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "fwd+bwd Msplats/sec at 1M surfels/1080p"
+UNIT = "Msplats/s"
+
+
+def algorithmic_bytes(P, V, R, W, H):
+    """SURVEY §8(d) / BASELINE.md §2.3 per-stage algorithmic bytes."""
+    N = W * H
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    return {
+        "preprocess_fwd": 48 * P + 271 * V + 8 * P,
+        "duplicate_with_keys": 20 * V + 12 * R,
+        "sort": 24 * R,
+        "identify_tile_ranges": 8 * R + 8 * tiles,
+        "render_fwd": 76 * R + 60 * N,
+        "render_bwd": 76 * R + 60 * N + 72 * R,
+        "preprocess_bwd": 343 * V + 240 * V,
+    }
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_oracle_run(scene_np, cam_np, gc, go, P, max_seconds=25.0):
+    """C-oracle (OpenMP, all host cores) fwd+bwd.  Full workload if it fits the time budget, else a
+    bounded sample: a band of tile rows of the same frame (all P splats are still preprocessed)."""
+    import numpy as np
+    from oracle import surfel_oracle as O
+    O.build()
+    bg = np.zeros(3, np.float32)
+    gy = (cam_np["H"] + 15) // 16
+    # probe with a thin band to estimate the cost of the full frame
+    probe_rows = max(1, gy // 16)
+    r0 = (gy - probe_rows) // 2
+    t0 = time.perf_counter()
+    pre, binned, img = O.forward(scene_np, cam_np, bg, row0=r0, row1=r0 + probe_rows)
+    O.backward(scene_np, cam_np, bg, pre, binned, img, gc, go)
+    t_probe = time.perf_counter() - t0
+    est_full = t_probe * gy / probe_rows
+    if est_full <= max_seconds:
+        rows, r0 = gy, 0
+    else:
+        rows = max(probe_rows, int(gy * max_seconds / est_full))
+        r0 = (gy - rows) // 2
+    t0 = time.perf_counter()
+    pre, binned, img = O.forward(scene_np, cam_np, bg, row0=r0, row1=r0 + rows)
+    O.backward(scene_np, cam_np, bg, pre, binned, img, gc, go)
+    dt = time.perf_counter() - t0
+    frac = rows / gy
+    sample = (f"full frame, {P} splats" if rows == gy else
+              f"tile rows [{r0},{r0 + rows}) of {gy} ({frac:.3f} of the frame; all {P} splats preprocessed); "
+              f"value = P*fraction/t")
+    return P * frac / dt / 1e6, dt, sample
+
+
+def run_reference(args, rank, world):
+    """Reference arm: CPU restatement of the reference rasterizer on the host cores."""
+    if rank != 0:
+        return
+    import numpy as np
+    import surfel_scenes as S
+    P, W, H = S.CONFIGS[args.workload]
+    scene, cam = S.named(args.workload)
+    gc, go = S.make_cotangents(W, H, S.CONFIG_SEED[args.workload])
+    sn, cn = S.to_numpy(scene), S.to_numpy(cam)
+    cores = os.cpu_count()
+    per_step = max(2.0, min(25.0, 150.0 / max(1, args.steps + args.warmup)))
+    vals, sample = [], ""
+    for i in range(args.warmup + args.steps):
+        v, dt, sample = cpu_oracle_run(sn, cn, gc.numpy(), go.numpy(), P, max_seconds=per_step)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals])) * 1e3
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {P} surfels, {W}x{H}, SH degree 3, fwd+bwd"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference CUDA rasterizer is not vendored in /root/reference; this is the CPU restatement (oracle/)",
+    }
+    print(json.dumps(out))
+
+
+def run_ours(args, rank, local_rank, world):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import surfel_scenes as S
+    import diff_surfel_rasterization as dsr
+    from diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer, _cabi
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _cabi.load()
+    P, W, H = S.CONFIGS[args.workload]
+    if args.splats:
+        P = args.splats
+    cam = S.make_camera(W, H)
+    # independent views: every rank renders its own statistically identical scene/view
+    scene = S.make_scene(P, W, H, S.CONFIG_SEED[args.workload] + 1000 * rank)
+    gc_h, go_h = S.make_cotangents(W, H, S.CONFIG_SEED[args.workload] + rank)
+    names = ["means3D", "scales", "rotations", "opacities", "shs"]
+    host_in = {k: scene[k].pin_memory() for k in names}
+    host_gc, host_go = gc_h.pin_memory(), go_h.pin_memory()
+    bg = torch.zeros(3, device=dev)
+    rs = GaussianRasterizationSettings(
+        image_height=H, image_width=W, tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"], bg=bg, scale_modifier=1.0,
+        viewmatrix=cam["viewmatrix"].to(dev), projmatrix=cam["projmatrix"].to(dev), sh_degree=3,
+        campos=cam["campos"].to(dev), prefiltered=False, debug=False)
+    rast = GaussianRasterizer(rs)
+    leaf = {k: host_in[k].to(dev).requires_grad_(True) for k in names}
+    means2D = torch.zeros(P, 3, device=dev, requires_grad=True)
+    gc, go = host_gc.to(dev), host_go.to(dev)
+
+    def step(inp, m2d, gcd, god):
+        for t in list(inp.values()) + [m2d]:
+            t.grad = None
+        color, radii, allmap = rast(means3D=inp["means3D"], means2D=m2d, shs=inp["shs"], opacities=inp["opacities"],
+                                    scales=inp["scales"], rotations=inp["rotations"])
+        torch.autograd.backward([color, allmap], [gcd, god])
+        return color, radii, allmap
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-input throughput ("value") ----
+    for _ in range(args.warmup):
+        color, radii, allmap = step(leaf, means2D, gc, go)
+    torch.cuda.synchronize()
+    V = int((radii > 0).sum())
+    R = int(dsr.last_num_rendered())
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    lib.surfel_profile_enable(1)
+    n_stage = lib.surfel_profile_num_stages()
+    import ctypes
+    ms_arr, cnt_arr = (ctypes.c_double * n_stage)(), (ctypes.c_int * n_stage)()
+    lib.surfel_profile_read(ms_arr, cnt_arr)   # drain
+    launches0 = lib.surfel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step(leaf, means2D, gc, go)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = int(lib.surfel_launch_count() - launches0)
+    lib.surfel_profile_enable(0)
+    lib.surfel_profile_read(ms_arr, cnt_arr)
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = e0.elapsed_time(e1)
+    tt = torch.tensor([t_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    barrier()
+    t_ms = float(tt.item())
+    ms_per_step = t_ms / args.steps
+    value = world * P / (ms_per_step * 1e-3) / 1e6
+
+    stage = {lib.surfel_profile_stage_name(i).decode(): (ms_arr[i], cnt_arr[i]) for i in range(n_stage) if cnt_arr[i]}
+    per_step = {k: v[0] / args.steps for k, v in stage.items()}            # ms per step, all launches
+    per_launch = {k: v[0] / v[1] for k, v in stage.items()}                # ms per launch
+    alg = algorithmic_bytes(P, V, R, W, H)
+    alg_launch = dict(alg)                                                 # bytes per LAUNCH
+    alg_launch["sort_onesweep_pass"] = 24 * R                              # one read + one write of the pairs
+    alg_launch["sort_histogram"] = 8 * R
+    peak, peak_src = measured_peak()
+    dom = max(per_step, key=lambda k: per_step[k])
+    achieved = alg_launch[dom] / (per_launch[dom] * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom)
+        except Exception:
+            traffic = None
+    b_alg = sum(alg.values())
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_launch[dom], "kernel_ms_per_launch": per_launch[dom],
+                "kernel_share_of_step": per_step[dom] / ms_per_step,
+                "pipeline": {"algorithmic_bytes": b_alg, "ms": ms_per_step,
+                             "achieved": b_alg / (ms_per_step * 1e-3) / 1e9,
+                             "frac": b_alg / (ms_per_step * 1e-3) / 1e9 / peak},
+                "stage_ms_per_step": {k: round(v, 4) for k, v in per_step.items()},
+                "stage_frac_of_peak": {k: round(alg_launch[k] / (per_launch[k] * 1e-3) / 1e9 / peak, 4)
+                                       for k in per_launch if k in alg_launch}}
+
+    # ---- end to end with HOST buffers (H2D of every input, D2H of outputs + gradients) ----
+    host_out = {"color": torch.empty(3, H, W).pin_memory(), "allmap": torch.empty(7, H, W).pin_memory(),
+                "radii": torch.empty(P, dtype=torch.int32).pin_memory()}
+    host_grad = {k: torch.empty_like(scene[k]).pin_memory() for k in names}
+    host_grad["means2D"] = torch.empty(P, 3).pin_memory()
+    h2d = sum(t.numel() * t.element_size() for t in host_in.values()) + host_gc.numel() * 4 + host_go.numel() * 4
+    d2h = sum(t.numel() * t.element_size() for t in list(host_out.values()) + list(host_grad.values()))
+
+    def e2e_step():
+        inp = {k: host_in[k].to(dev, non_blocking=True).requires_grad_(True) for k in names}
+        m2d = torch.zeros(P, 3, device=dev, requires_grad=True)
+        gcd, god = host_gc.to(dev, non_blocking=True), host_go.to(dev, non_blocking=True)
+        color, radii_, allmap = step(inp, m2d, gcd, god)
+        host_out["color"].copy_(color.detach(), non_blocking=True)
+        host_out["allmap"].copy_(allmap.detach(), non_blocking=True)
+        host_out["radii"].copy_(radii_, non_blocking=True)
+        for k in names:
+            host_grad[k].copy_(inp[k].grad, non_blocking=True)
+        host_grad["means2D"].copy_(m2d.grad, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(max(1, min(args.warmup, 3))):
+            e2e_step()
+        barrier()
+        e2e_steps = max(3, min(args.steps, 10))
+        e0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize()
+        te = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        barrier()
+        e2e_ms = float(te.item()) / e2e_steps
+        e2e = {"value": world * P / (e2e_ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": e2e_ms, "steps": e2e_steps,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+
+    # ---- CPU baseline on rank 0 (N == 1 only) ----
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sn, cn = S.to_numpy(scene), S.to_numpy(cam)
+        v, dt, sample = cpu_oracle_run(sn, cn, gc_h.numpy(), go_h.numpy(), P, max_seconds=20.0)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                        "sample": sample, "seconds": dt}
+        try:   # the "pure-Python surfel rasterizer" of BASELINE.md §2.1 (dense PyTorch, config 1, forward)
+            from oracle import dense_torch as DT
+            s1, c1 = S.named("config1")
+            torch.set_num_threads(min(32, os.cpu_count()))
+            ts = []
+            for _ in range(1):
+                t0 = time.perf_counter()
+                with torch.no_grad():
+                    DT.render(s1["means3D"], s1["scales"], s1["rotations"], s1["opacities"], s1["shs"], c1["viewmatrix"],
+                              c1["projmatrix"], c1["campos"], torch.zeros(3), c1["W"], c1["H"], pixel_chunk=8192)
+                ts.append(time.perf_counter() - t0)
+            cpu_baseline["pure_python_config1_forward"] = {"ms": sorted(ts)[0] * 1e3, "Msplats_per_s": 1000 / sorted(ts)[0] / 1e6,
+                                                           "what": "dense PyTorch surfel rasterizer, 1k surfels 256x256, forward only"}
+        except Exception as ex:   # never let the optional extra break the bench line
+            cpu_baseline["pure_python_config1_forward"] = {"error": str(ex)[:200]}
+
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {P} surfels, {W}x{H}, SH degree 3, fwd+bwd, one view per GPU",
+                       "visible": V, "instances": R, "parallelism": f"view-parallel x{world} (no collective)",
+                       "l2_policy": "inputs larger than L2 (232 MB of splat parameters + 83 MB of outputs per step vs 126 MB L2)"},
+            "e2e": e2e, "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
+            "roofline": roofline, "clocks": clocks,
+        }
+        if cpu_baseline is not None:
+            out["cpu_baseline"] = cpu_baseline
+        print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="headline")
+    ap.add_argument("--splats", type=int, default=0, help="override P (debugging only)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_ours(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

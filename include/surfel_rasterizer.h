@@ -134,6 +134,16 @@ size_t surfel_sort_temp_bytes(size_t n);
 int surfel_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
                       size_t n, int end_bit, void* temp, int* result_in_b, void* stream);
 
+/* Instrumentation used by bench.py: number of kernels this library has launched in this process,
+ * and optional per-stage CUDA-event timing (events recorded on the launching stream around each
+ * kernel while enabled; surfel_profile_read() waits for them and returns summed ms / launch counts
+ * per stage since the previous read). */
+unsigned long long surfel_launch_count(void);
+void surfel_profile_enable(int on);
+int surfel_profile_num_stages(void);
+const char* surfel_profile_stage_name(int stage);
+int surfel_profile_read(double* ms_out, int* count_out);
+
 #ifdef __cplusplus
 }
 #endif
