@@ -23,10 +23,19 @@ __constant__ float b_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.45
 constexpr float SH_C0 = 0.28209479177387814f;
 constexpr float SH_C1 = 0.4886025119029199f;
 
+constexpr int kRowQuads = 13;   // 12 data quads + 1 pad: conflict-free 128-bit row access
+
+// kStaged: SH rows (in) and dL_dsh rows (out) travel through shared memory so that every global
+// access is a fully coalesced 128-bit transaction (M == 16, degree 3, 16-byte aligned tensors);
+// otherwise each thread addresses its own rows directly (any M / degree).
+template <bool kStaged>
 __global__ void __launch_bounds__(128) preprocess_bwd_kernel(PreBwdParams p) {
+    __shared__ float4 s_rows[kStaged ? 4 * 32 * kRowQuads : 1];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= p.P) return;
-    const bool visible = p.radii[idx] > 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool in_range = idx < p.P;
+    if (!kStaged && !in_range) return;
+    const bool visible = in_range && p.radii[idx] > 0;
     const bool geom = p.transMat_precomp == nullptr;
     const bool has_sh = !p.has_colors_precomp && p.shs != nullptr;
 
@@ -119,10 +128,31 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(PreBwdParams p) {
 
     // 3. SH backward (writes the full dL_dsh row; zeros when culled / beyond the active degree)
     if (has_sh) {
-        float* gsh = p.dL_dsh + (size_t)idx * 3 * p.M;
+        float v[48];                       // staged path: sh row in, dL_dsh row out (in place)
+        float4* wrow = s_rows + (kStaged ? (warp * 32 + lane) * kRowQuads : 0);
+        const int warp_first = blockIdx.x * blockDim.x + warp * 32;
+        if (kStaged) {
+            // cooperative, fully coalesced load of the warp's 32 SH rows (only rows of visible splats)
+            const unsigned vis_mask = __ballot_sync(0xffffffffu, visible);
+            const float4* src = reinterpret_cast<const float4*>(p.shs) + (size_t)warp_first * 12;
+            float4* dst = s_rows + warp * 32 * kRowQuads;
+            for (int f = lane; f < 32 * 12; f += 32) {
+                const int row = f / 12, q = f - row * 12;
+                if ((vis_mask >> row) & 1u) dst[row * kRowQuads + q] = ld_nc_f4(src + f);
+            }
+            __syncwarp();
+            if (visible) {
+#pragma unroll
+                for (int q = 0; q < 12; q++) {
+                    const float4 t = wrow[q];
+                    v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+                }
+            }
+        }
+        float* gsh = kStaged ? nullptr : p.dL_dsh + (size_t)idx * 3 * p.M;
+        const float* shg = kStaged ? nullptr : p.shs + (size_t)idx * 3 * p.M;
         const int ncoef_active = visible ? (p.D + 1) * (p.D + 1) : 0;
         if (visible) {
-            const float* sh = p.shs + (size_t)idx * 3 * p.M;
             const uint8_t cb = p.clamped[idx];
             const float dR[3] = {(cb & 1) ? 0.0f : gc[0], (cb & 2) ? 0.0f : gc[1], (cb & 4) ? 0.0f : gc[2]};
             const float dox = px - p.campos[0], doy = py - p.campos[1], doz = pz - p.campos[2];
@@ -130,27 +160,31 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(PreBwdParams p) {
             const float invl = 1.0f / sqrtf(sq);
             const float x = dox * invl, y = doy * invl, z = doz * invl;
             float ddx = 0, ddy = 0, ddz = 0;
-#define GS(i, val) do { const float _v = (val); gsh[3 * (i)] = _v * dR[0]; gsh[3 * (i) + 1] = _v * dR[1]; gsh[3 * (i) + 2] = _v * dR[2]; } while (0)
-#define DOT(i) (dR[0] * sh[3 * (i)] + dR[1] * sh[3 * (i) + 1] + dR[2] * sh[3 * (i) + 2])
+#define SHV(i, c) (kStaged ? v[3 * (i) + (c)] : shg[3 * (i) + (c)])
+#define GS(i, val) do { const float _v = (val); if (kStaged) { v[3 * (i)] = _v * dR[0]; v[3 * (i) + 1] = _v * dR[1]; v[3 * (i) + 2] = _v * dR[2]; } \
+                        else { gsh[3 * (i)] = _v * dR[0]; gsh[3 * (i) + 1] = _v * dR[1]; gsh[3 * (i) + 2] = _v * dR[2]; } } while (0)
+#define DOT(i) (dR[0] * SHV(i, 0) + dR[1] * SHV(i, 1) + dR[2] * SHV(i, 2))
+            // every DOT(i) is taken before GS(i) overwrites coefficient i (in-place row)
             GS(0, SH_C0);
             if (p.D > 0) {
+                const float d1 = DOT(1), d2 = DOT(2), d3 = DOT(3);
                 GS(1, -SH_C1 * y); GS(2, SH_C1 * z); GS(3, -SH_C1 * x);
-                ddx += -SH_C1 * DOT(3); ddy += -SH_C1 * DOT(1); ddz += SH_C1 * DOT(2);
+                ddx += -SH_C1 * d3; ddy += -SH_C1 * d1; ddz += SH_C1 * d2;
                 if (p.D > 1) {
                     const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                    const float d4 = DOT(4), d5 = DOT(5), d6 = DOT(6), d7 = DOT(7), d8 = DOT(8);
                     GS(4, b_SH_C2[0] * xy); GS(5, b_SH_C2[1] * yz); GS(6, b_SH_C2[2] * (2.0f * zz - xx - yy));
                     GS(7, b_SH_C2[3] * xz); GS(8, b_SH_C2[4] * (xx - yy));
-                    const float d4 = DOT(4), d5 = DOT(5), d6 = DOT(6), d7 = DOT(7), d8 = DOT(8);
                     ddx += b_SH_C2[0] * y * d4 + b_SH_C2[2] * 2.0f * -x * d6 + b_SH_C2[3] * z * d7 + b_SH_C2[4] * 2.0f * x * d8;
                     ddy += b_SH_C2[0] * x * d4 + b_SH_C2[1] * z * d5 + b_SH_C2[2] * 2.0f * -y * d6 + b_SH_C2[4] * 2.0f * -y * d8;
                     ddz += b_SH_C2[1] * y * d5 + b_SH_C2[2] * 4.0f * z * d6 + b_SH_C2[3] * x * d7;
                     if (p.D > 2) {
+                        const float d9 = DOT(9), d10 = DOT(10), d11 = DOT(11), d12 = DOT(12), d13 = DOT(13), d14 = DOT(14), d15 = DOT(15);
                         GS(9, b_SH_C3[0] * y * (3.0f * xx - yy)); GS(10, b_SH_C3[1] * xy * z);
                         GS(11, b_SH_C3[2] * y * (4.0f * zz - xx - yy));
                         GS(12, b_SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy));
                         GS(13, b_SH_C3[4] * x * (4.0f * zz - xx - yy)); GS(14, b_SH_C3[5] * z * (xx - yy));
                         GS(15, b_SH_C3[6] * x * (xx - 3.0f * yy));
-                        const float d9 = DOT(9), d10 = DOT(10), d11 = DOT(11), d12 = DOT(12), d13 = DOT(13), d14 = DOT(14), d15 = DOT(15);
                         ddx += b_SH_C3[0] * d9 * 6.0f * xy + b_SH_C3[1] * d10 * yz + b_SH_C3[2] * d11 * -2.0f * xy +
                                b_SH_C3[3] * d12 * -6.0f * xz + b_SH_C3[4] * d13 * (-3.0f * xx + 4.0f * zz - yy) +
                                b_SH_C3[5] * d14 * 2.0f * xz + b_SH_C3[6] * d15 * 3.0f * (xx - yy);
@@ -165,13 +199,33 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(PreBwdParams p) {
             }
 #undef GS
 #undef DOT
+#undef SHV
             const float inv3 = invl * invl * invl;
             g3[0] += ((doy * doy + doz * doz) * ddx - doy * dox * ddy - doz * dox * ddz) * inv3;
             g3[1] += (-dox * doy * ddx + (dox * dox + doz * doz) * ddy - doz * doy * ddz) * inv3;
             g3[2] += (-dox * doz * ddx - doy * doz * ddy + (dox * dox + doy * doy) * ddz) * inv3;
         }
-        for (int i = 3 * ncoef_active; i < 3 * p.M; i++) gsh[i] = 0.0f;
+        if (kStaged) {
+            // row back to shared memory (zeros for culled splats and for coefficients beyond the
+            // active degree), then one coalesced sweep to HBM
+#pragma unroll
+            for (int i = 0; i < 48; i++) if (i >= 3 * ncoef_active) v[i] = 0.0f;
+#pragma unroll
+            for (int q = 0; q < 12; q++)
+                wrow[q] = visible ? make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+            const int nrows = min(32, p.P - warp_first);
+            float4* dstg = reinterpret_cast<float4*>(p.dL_dsh) + (size_t)warp_first * 12;
+            const float4* srcw = s_rows + warp * 32 * kRowQuads;
+            for (int f = lane; f < nrows * 12; f += 32) {
+                const int row = f / 12, q = f - row * 12;
+                dstg[f] = srcw[row * kRowQuads + q];
+            }
+        } else {
+            for (int i = 3 * ncoef_active; i < 3 * p.M; i++) gsh[i] = 0.0f;
+        }
     }
+    if (!in_range) return;
 
     // 4. outputs (every row written)
     float* o;
@@ -194,7 +248,10 @@ __global__ void __launch_bounds__(128) preprocess_bwd_kernel(PreBwdParams p) {
 int launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t stream) {
     if (p.P <= 0) return 0;
     LaunchScope scope(kStPreBwd, stream);
-    preprocess_bwd_kernel<<<(p.P + 127) / 128, 128, 0, stream>>>(p);
+    const bool staged = !p.has_colors_precomp && p.shs != nullptr && p.D <= 3 && p.M == 16 &&
+                        reinterpret_cast<uintptr_t>(p.shs) % 16 == 0 && reinterpret_cast<uintptr_t>(p.dL_dsh) % 16 == 0;
+    if (staged) preprocess_bwd_kernel<true><<<(p.P + 127) / 128, 128, 0, stream>>>(p);
+    else        preprocess_bwd_kernel<false><<<(p.P + 127) / 128, 128, 0, stream>>>(p);
     SURFEL_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_kernel(PreFwdParams 
     }
 
     // ---- write per-splat state ----
+    __syncwarp();   // every lane has consumed its SH row: the panel is reused for the records
     if (idx < p.P) {
         p.radii[idx] = visible ? radius_i : 0;
         p.tiles_touched[idx] = tt;
@@ -263,13 +264,26 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_kernel(PreFwdParams 
                     bx0 = by0 = -3.0e38f; bx1 = by1 = 3.0e38f;  // unbounded conic: never culled
                 }
             }
-            float4* r = p.rec + (size_t)idx * kRecQuads;
+            // record -> the warp's shared-memory panel (7-quad stride: conflict-free); the warp then
+            // streams its 32 records (3 KB contiguous) to HBM with fully coalesced 128-bit stores
+            float4* r = s_sh + warp * 32 * kShRowQuads + lane * 7;
             r[0] = make_float4(tm[0], tm[1], tm[2], tm[3]);
             r[1] = make_float4(tm[4], tm[5], tm[6], tm[7]);
             r[2] = make_float4(tm[8], cx, cy, opa);
             r[3] = make_float4(nrm[0], nrm[1], nrm[2], pvz);
             r[4] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
             r[5] = make_float4(bx0, by0, bx1, by1);
+        }
+    }
+    {
+        __syncwarp();
+        const int warp_first = (int)(bid * kPreBlock) + warp * 32;
+        const int nrows = min(32, p.P - warp_first);
+        const float4* src = s_sh + warp * 32 * kShRowQuads;
+        float4* dst = p.rec + (size_t)warp_first * kRecQuads;
+        for (int f = lane; f < nrows * kRecQuads; f += 32) {
+            const int row = f / kRecQuads, q = f - row * kRecQuads;
+            if ((vis_mask >> row) & 1u) dst[f] = src[row * 7 + q];
         }
     }
 
@@ -339,7 +353,7 @@ int launch_preprocess_fwd(const PreFwdParams& p, cudaStream_t stream) {
     const int blocks = (p.P + kPreBlock - 1) / kPreBlock;
     SURFEL_CUDA_OK(cudaMemsetAsync(p.scan_status, 0, (size_t)(blocks + 1) * 8, stream));
     SURFEL_CUDA_OK(cudaMemsetAsync(p.counters, 0, 64, stream));
-    const bool vec4 = p.colors_precomp == nullptr && p.D == 3 && p.M == 16 &&
+    const bool vec4 = p.colors_precomp == nullptr && p.D <= 3 && p.M == 16 &&
                       (reinterpret_cast<uintptr_t>(p.shs) % 16 == 0);
     LaunchScope scope(kStPreFwd, stream);
     if (vec4) preprocess_fwd_kernel<true><<<blocks, kPreBlock, 0, stream>>>(p);

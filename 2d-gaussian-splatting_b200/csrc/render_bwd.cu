@@ -76,10 +76,12 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderParams p) {
 #pragma unroll
     for (int w = 0; w < 8; w++) cta_max = max(cta_max, s_max[w]);
 
-    float T = T_final, last_alpha = 0, last_dL_dT = 0;
-    float last_c0 = 0, last_c1 = 0, last_c2 = 0, acc_c0 = 0, acc_c1 = 0, acc_c2 = 0;
-    float last_depth = 0, acc_depth = 0, acc_alpha = 0;
-    float last_n0 = 0, last_n1 = 0, last_n2 = 0, acc_n0 = 0, acc_n1 = 0, acc_n2 = 0;
+    // Per-pixel replay state.  All blended outputs are linear in the weights w_j = alpha_j*T_j, so
+    // with the per-pair scalar "value"
+    //     v_j = rgb_j.dL_dC + depth_j*dL_dD + dL_dA + n_j.dL_dN + dL_dweight_j      (dL/dw_j)
+    // the A.4 suffix recurrences (accum_rec for colour, depth, alpha, normal and last_dL_dT) collapse
+    // into ONE accumulator S = sum_{j>i} w_j v_j:   dL/dalpha_i = T_i v_i - S/(1-alpha_i) + bg term.
+    float T = T_final, S = 0.0f;
     constexpr float kMScale = kFar / (kFar - kNear);
     constexpr float kDmScale = (kFar * kNear) / (kFar - kNear);
 
@@ -124,35 +126,18 @@ __global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderParams p) {
                     const float inv1ma = fast_rcp(one_m);
                     T = T * inv1ma;
                     const float w = alpha * T;
-                    const float la = last_alpha, ola = 1.0f - last_alpha;
-                    // colour
-                    acc_c0 = la * last_c0 + ola * acc_c0; last_c0 = q4.x;
-                    acc_c1 = la * last_c1 + ola * acc_c1; last_c1 = q4.y;
-                    acc_c2 = la * last_c2 + ola * acc_c2; last_c2 = q4.z;
-                    float dL_dalpha = (q4.x - acc_c0) * dpix0 + (q4.y - acc_c1) * dpix1 + (q4.z - acc_c2) * dpix2;
-                    // distortion + median depth
                     const float inv_d = fast_rcp(e.depth);
                     const float m_d = kMScale * (1.0f - kNear * inv_d);
                     const float dmd_dd = kDmScale * inv_d * inv_d;
-                    float dL_dz = (index == median_index) ? dL_dmedian : 0.0f;
                     const float dL_dweight = (final_D2 + m_d * m_d * final_A - 2.0f * m_d * final_D) * dL_dreg;
-                    dL_dalpha += dL_dweight - last_dL_dT;
-                    last_dL_dT = dL_dweight * alpha + one_m * last_dL_dT;
+                    float v = dL_dweight + dL_daccum;
+                    v = fmaf(q4.x, dpix0, v); v = fmaf(q4.y, dpix1, v); v = fmaf(q4.z, dpix2, v);
+                    v = fmaf(e.depth, dL_ddepth, v);
+                    v = fmaf(q3.x, dN0, v); v = fmaf(q3.y, dN1, v); v = fmaf(q3.z, dN2, v);
+                    const float dL_dalpha = T * v - (S - bgT) * inv1ma;
+                    S = fmaf(w, v, S);
+                    float dL_dz = (index == median_index) ? dL_dmedian : 0.0f;
                     dL_dz += 2.0f * w * (m_d * final_A - final_D) * dL_dreg * dmd_dd;
-                    // expected depth, alpha
-                    acc_depth = la * last_depth + ola * acc_depth; last_depth = e.depth;
-                    dL_dalpha += (e.depth - acc_depth) * dL_ddepth;
-                    acc_alpha = la + ola * acc_alpha;
-                    dL_dalpha += (1.0f - acc_alpha) * dL_daccum;
-                    // normal
-                    acc_n0 = la * last_n0 + ola * acc_n0; last_n0 = q3.x;
-                    acc_n1 = la * last_n1 + ola * acc_n1; last_n1 = q3.y;
-                    acc_n2 = la * last_n2 + ola * acc_n2; last_n2 = q3.z;
-                    dL_dalpha += (q3.x - acc_n0) * dN0 + (q3.y - acc_n1) * dN1 + (q3.z - acc_n2) * dN2;
-
-                    dL_dalpha *= T;
-                    last_alpha = alpha;
-                    dL_dalpha += bgT * inv1ma;
                     const float dL_dG = q2.w * dL_dalpha;
                     dL_dz += w * dL_ddepth;
                     float g0 = 0, g1 = 0, g2 = 0, g3 = 0, g4 = 0, g5 = 0, g6 = 0, g7 = 0, g8, g9 = 0, g10 = 0;
