@@ -68,7 +68,7 @@ constexpr int kShRowQuads = 13;                 // 12 data quads + 1 pad: confli
 constexpr int kShRowFloatsScalar = 49;          // scalar path stride (odd: conflict-free LDS.32)
 
 template <bool kVec4>
-__global__ void __launch_bounds__(kPreBlock) preprocess_fwd_kernel(PreFwdParams p) {
+__global__ void __launch_bounds__(kPreBlock, 6) preprocess_fwd_kernel(PreFwdParams p) {
     __shared__ float4 s_sh[(kPreBlock / 32) * 32 * kShRowQuads];
     __shared__ int s_rows[kPreBlock];            // per warp: compacted list of visible lanes
     __shared__ uint32_t s_warp_sum[kPreBlock / 32];
@@ -163,6 +163,25 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_kernel(PreFwdParams 
         }
         if (visible) opa = p.opacities[idx];
     }
+
+    // ---- block inclusive scan of tiles_touched; the block aggregate is published NOW, before the
+    // SH work, so that by the time successor blocks look back (at their very end) it is long there ----
+    uint32_t incl = tt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp_sum[warp] = incl;
+    __syncthreads();
+    uint32_t warp_excl = 0, block_total = 0;
+#pragma unroll
+    for (int w = 0; w < kPreBlock / 32; w++) {
+        const uint32_t s = s_warp_sum[w];
+        if (w < warp) warp_excl += s;
+        block_total += s;
+    }
+    if (tid == 0) st_status(p.scan_status + bid, (bid == 0 ? kFlagPrefix : kFlagAgg) | block_total);
 
     // ---- SH -> RGB for surviving splats (rows staged warp-cooperatively) ----
     float rgb[3] = {0, 0, 0};
@@ -287,29 +306,11 @@ __global__ void __launch_bounds__(kPreBlock) preprocess_fwd_kernel(PreFwdParams 
         }
     }
 
-    // ---- block inclusive scan of tiles_touched + decoupled look-back across blocks ----
-    uint32_t incl = tt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) s_warp_sum[warp] = incl;
-    __syncthreads();
-    uint32_t warp_excl = 0, block_total = 0;
-#pragma unroll
-    for (int w = 0; w < kPreBlock / 32; w++) {
-        const uint32_t s = s_warp_sum[w];
-        if (w < warp) warp_excl += s;
-        block_total += s;
-    }
+    // ---- decoupled look-back across blocks (predecessor aggregates were published early) ----
     if (warp == 0) {
         unsigned long long* status = p.scan_status;
         uint32_t excl = 0;
-        if (bid == 0) {
-            if (lane == 0) st_status(status + 0, kFlagPrefix | block_total);
-        } else {
-            if (lane == 0) st_status(status + bid, kFlagAgg | block_total);
+        if (bid != 0) {
             int look = (int)bid - 1;
             while (true) {
                 const int j = look - lane;

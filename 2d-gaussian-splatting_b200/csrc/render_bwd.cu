@@ -21,10 +21,13 @@
 
 namespace surfel {
 
+#ifndef SURFEL_BWD_BLOCKS
+#define SURFEL_BWD_BLOCKS 4
+#endif
 constexpr int kBatchB = 256;
 constexpr int kPanelRow = kGradFloats;            // 20 floats = 80 B per contributing lane
 
-__global__ void __launch_bounds__(256, 3) render_bwd_kernel(RenderParams p) {
+__global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(RenderParams p) {
     __shared__ float4 s_rec[kRecQuads * kBatchB];            // [quad][slot]
     __shared__ uint32_t s_id[kBatchB];
     __shared__ __align__(16) float s_panel[8 * 32 * kPanelRow];

@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libsurfel_b200.so")
+LIB_PATH = os.environ.get("SURFEL_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libsurfel_b200.so")
 
 c_void_p, c_int, c_uint32, c_size_t, c_float = (ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32,
                                                 ctypes.c_size_t, ctypes.c_float)
