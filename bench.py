@@ -62,52 +62,71 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (20 ms period; every line
+    is stamped on receipt so that only samples inside [mark_start, mark_stop] are reported)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.t0, self.t1 = index, None, [], None, None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
+            t_end = time.time() + 3.0
+            while not self.lines and time.time() < t_end:     # wait for the first sample
+                time.sleep(0.01)
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_stop(self):
+        self.t1 = time.time()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             pass
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
-        sm.sort()
+
+        def parse(lines):
+            sm, mx, reasons = [], [], set()
+            for _, ln in lines:
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 7:
+                    continue
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            return sorted(sm), mx, reasons
+        inside = [x for x in self.lines if self.t0 is not None and self.t0 <= x[0] <= (self.t1 or 1e30) + 0.02]
+        note = "samples inside the timed region"
+        if len(inside) < 2:       # region shorter than the sampling period: widen to +-0.3 s around it
+            inside = [x for x in self.lines if self.t0 is not None and self.t0 - 0.3 <= x[0] <= (self.t1 or 1e30) + 0.3]
+            note = "timed region shorter than 2 sampling periods: samples within +-0.3 s of it (GPU busy with the same loop)"
+        sm, mx, reasons = parse(inside)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "note": note}
 
 
 def cpu_oracle_run(scene_np, cam_np, gc, go, P, max_seconds=25.0):
@@ -153,8 +172,12 @@ def run_reference(args, rank, world):
     gc, go = S.make_cotangents(W, H, S.CONFIG_SEED[args.workload])
     sn, cn = S.to_numpy(scene), S.to_numpy(cam)
     cores = os.cpu_count()
-    per_step = max(2.0, min(25.0, 150.0 / max(1, args.steps + args.warmup)))
+    # CPU steps are seconds long: run at most 6 timed + 1 warm-up sample however large K is, each
+    # bounded so that the whole arm ends within a few minutes; the JSON line reports the real counts.
+    n_warm, n_steps = min(args.warmup, 1), min(args.steps, 6)
+    per_step = max(2.0, min(25.0, 150.0 / max(1, n_steps + n_warm)))
     vals, sample = [], ""
+    args.warmup, args.steps = n_warm, n_steps
     for i in range(args.warmup + args.steps):
         v, dt, sample = cpu_oracle_run(sn, cn, gc.numpy(), go.numpy(), P, max_seconds=per_step)
         if i >= args.warmup:
@@ -219,15 +242,15 @@ def run_ours(args, rank, local_rank, world):
         torch.cuda.synchronize()
 
     # ---- resident-input throughput ("value") ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for _ in range(args.warmup):
         color, radii, allmap = step(leaf, means2D, gc, go)
     torch.cuda.synchronize()
     V = int((radii > 0).sum())
     R = int(dsr.last_num_rendered())
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
     lib.surfel_profile_enable(1)
     n_stage = lib.surfel_profile_num_stages()
     import ctypes
@@ -235,11 +258,13 @@ def run_ours(args, rank, local_rank, world):
     lib.surfel_profile_read(ms_arr, cnt_arr)   # drain
     launches0 = lib.surfel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_start()
     e0.record()
     for _ in range(args.steps):
         step(leaf, means2D, gc, go)
     e1.record()
     torch.cuda.synchronize()
+    sampler.mark_stop()
     launches = int(lib.surfel_launch_count() - launches0)
     lib.surfel_profile_enable(0)
     lib.surfel_profile_read(ms_arr, cnt_arr)
@@ -364,8 +389,8 @@ def run_ours(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="headline")
     ap.add_argument("--splats", type=int, default=0, help="override P (debugging only)")
