@@ -23,6 +23,7 @@ SOURCES = {
     "preprocess_bwd.cu": [],
     "binning.cu": [],
     "radix_sort.cu": [],
+    "bucket_sort.cu": [],
     "render_fwd.cu": [],
     "render_bwd.cu": [],
 }

@@ -3,6 +3,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
+#include <algorithm>
 
 #include "../../include/surfel_rasterizer.h"
 #include "common.cuh"
@@ -53,7 +55,7 @@ BinningLayout binning_layout(size_t R, int tiles) {
     L.vals_a = o;    o = align_up(o + r * 4, 256);
     L.vals_b = o;    o = align_up(o + r * 4, 256);
     L.ranges = o;    o = align_up(o + (size_t)tiles * 8, 256);
-    L.sort_temp = o; o = align_up(o + radix_sort_temp_bytes(r), 256);
+    L.sort_temp = o; o = align_up(o + std::max(radix_sort_temp_bytes(r), bucket_temp_bytes(tiles)), 256);
     L.total = o;
     return L;
 }
@@ -185,9 +187,30 @@ int surfel_render_forward(const surfel_settings_t* s, uint32_t R, const void* ge
     return launch_render_fwd(p, (cudaStream_t)stream);
 }
 
+int surfel_bin_bucket(const surfel_settings_t* s, int P, uint32_t R, const void* geom_ws,
+                      const int32_t* radii, void* binning_ws, int write_keys, void* stream) {
+    Frame f;
+    if (!frame_of(s, f)) return 1;
+    GeomLayout L = geom_layout(P);
+    const char* g = (const char*)geom_ws;
+    BinView v = bin_view(binning_ws, R, f);
+    // scratch pairs live in whichever key buffer does NOT receive the sorted keys
+    unsigned long long* pairs = (unsigned long long*)(v.k_sorted == v.k_a ? v.k_b : v.k_a);
+    return launch_bucket_binning(P, R, f.gx, f.gy, f.row0, f.row1, (const float4*)(g + L.rec), radii,
+                                 (const uint32_t*)(g + L.offsets), pairs, v.v_sorted,
+                                 write_keys ? (unsigned long long*)v.k_sorted : nullptr, v.ranges, v.temp,
+                                 (cudaStream_t)stream);
+}
+
 int surfel_forward_render(const surfel_settings_t* s, int P, uint32_t R, const int32_t* radii,
                           const void* geom_ws, void* binning_ws, void* image_ws, float* out_color,
                           float* out_others, void* stream) {
+    // SURFEL_SORT=radix selects the device-wide onesweep radix sort instead of the tile-bucketed path
+    static const bool use_radix = [] { const char* e = getenv("SURFEL_SORT"); return e && !strcmp(e, "radix"); }();
+    if (!use_radix) {
+        if (surfel_bin_bucket(s, P, R, geom_ws, radii, binning_ws, 0, stream)) return 1;
+        return surfel_render_forward(s, R, geom_ws, binning_ws, image_ws, out_color, out_others, stream);
+    }
     if (surfel_bin_duplicate(s, P, R, geom_ws, radii, binning_ws, stream)) return 1;
     if (surfel_bin_sort(s, R, binning_ws, stream)) return 1;
     return surfel_render_forward(s, R, geom_ws, binning_ws, image_ws, out_color, out_others, stream);

@@ -1,0 +1,296 @@
+// bucket_sort.cu — tile-bucketed binning: the production replacement for
+// duplicateWithKeys + device-wide radix sort + identifyTileRanges.
+//
+// The required result is the instance list sorted by (tile, depth bits, splat index) plus the
+// per-tile [start,end) ranges.  A device-wide LSD radix sort reaches it with 6-7 passes over
+// (u64,u32) pairs; on B200 at R ~ 2-3 M those passes are latency-bound (~38 us each, profiles/r1).
+// The structure of the key allows a two-level scheme with ONE scatter and ONE local sort:
+//   1. tile_count   : walk every block's flattened instance range, RED.add on the tile counters;
+//   2. tile_scan    : exclusive scan of the counters -> ranges (identifyTileRanges for free),
+//                     list of tiles too large for the fast sort;
+//   3. tile_scatter : same walk; claim a slot in the tile's bucket with an atomic and store
+//                     (depth_bits << 32 | splat_idx).  Arrival order inside a bucket is arbitrary;
+//   4. tile_sort    : one CTA per tile sorts its bucket in shared memory (bitonic network on the
+//                     64-bit (depth, idx) key — a total order, so the result is deterministic and
+//                     equals the stable radix sort's: depth ascending, ties by splat index) and
+//                     writes the point list (and, for tests, the full (tile|depth) keys);
+//      tiles above kSmallMax entries use a 1024-thread CTA with up to 128 KB of shared memory, and
+//      beyond that a global-memory bitonic sort (pathological inputs only; correct, slow).
+// Traffic: 8 B written + 8 B read + 4 B written per instance instead of ~150 B.
+#include <algorithm>
+#include "common.cuh"
+#include "kernels.h"
+#include "profile.h"
+
+namespace surfel {
+
+constexpr int kWalkBlock = 256;
+constexpr int kSmallMax = 2048;          // entries sorted by the 128-thread fast path (16 KB smem)
+constexpr int kLargeMax = 16384;         // entries sorted in 128 KB of dynamic smem by 1024 threads
+
+// Shared helper: block of 256 splats -> flattened instance walk.  F(tile, depth_bits, splat_idx).
+template <typename F>
+__device__ __forceinline__ void walk_instances(int P, int gx, int gy, int row0, int row1,
+                                               const float4* __restrict__ rec, const int* __restrict__ radii,
+                                               const uint32_t* __restrict__ offsets, F f) {
+    __shared__ uint32_t s_end[kWalkBlock];
+    __shared__ int s_x0[kWalkBlock], s_y0[kWalkBlock], s_w[kWalkBlock];
+    __shared__ uint32_t s_depth[kWalkBlock];
+    const int tid = threadIdx.x;
+    const int first = blockIdx.x * kWalkBlock;
+    const int idx = first + tid;
+    const uint32_t base = first == 0 ? 0u : offsets[first - 1];
+    const int last = min(P, first + kWalkBlock) - 1;
+    s_end[tid] = offsets[min(idx, last)];
+    int x0 = 0, y0 = 0, w = 1;
+    uint32_t dbits = 0;
+    if (idx < P) {
+        const int r = radii[idx];
+        if (r > 0) {
+            const float4 q2 = rec[(size_t)idx * kRecQuads + 2];
+            const float4 q3 = rec[(size_t)idx * kRecQuads + 3];
+            int x1, y1;
+            get_rect(q2.y, q2.z, r, gx, gy, row0, row1, x0, y0, x1, y1);
+            w = max(1, x1 - x0);
+            dbits = __float_as_uint(q3.w);
+        }
+    }
+    s_x0[tid] = x0; s_y0[tid] = y0; s_w[tid] = w; s_depth[tid] = dbits;
+    __syncthreads();
+    const uint32_t total = s_end[kWalkBlock - 1] - base;
+    for (uint32_t i = tid; i < total; i += kWalkBlock) {
+        const uint32_t g = base + i;
+        int lo = 0, hi = kWalkBlock - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (s_end[mid] > g) hi = mid; else lo = mid + 1;
+        }
+        const uint32_t start = lo == 0 ? base : s_end[lo - 1];
+        const uint32_t j = g - start;
+        const uint32_t ww = (uint32_t)s_w[lo];
+        const uint32_t ry = j / ww, rx = j - ry * ww;
+        const uint32_t tile = (uint32_t)(s_y0[lo] + (int)ry) * (uint32_t)gx + (uint32_t)(s_x0[lo] + (int)rx);
+        f(tile, s_depth[lo], (uint32_t)(first + lo));
+    }
+}
+
+__global__ void __launch_bounds__(kWalkBlock)
+tile_count_kernel(int P, int gx, int gy, int row0, int row1, const float4* __restrict__ rec,
+                  const int* __restrict__ radii, const uint32_t* __restrict__ offsets,
+                  uint32_t* __restrict__ tile_count) {
+    walk_instances(P, gx, gy, row0, row1, rec, radii, offsets,
+                   [&](uint32_t tile, uint32_t, uint32_t) { atomicAdd(tile_count + tile, 1u); });
+}
+
+// One block: exclusive scan of tile_count -> ranges; zero the fill cursors; collect big tiles.
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
+                 uint32_t* __restrict__ tile_fill, uint32_t* __restrict__ big_list,
+                 uint32_t* __restrict__ big_count) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_carry = 0; *big_count = 0; }
+    __syncthreads();
+    for (int base = 0; base < tiles; base += 1024) {
+        const int t = base + tid;
+        const uint32_t c = t < tiles ? tile_count[t] : 0u;
+        uint32_t incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t pre = s_carry;
+        for (int w = 0; w < warp; w++) pre += s_warp[w];
+        if (t < tiles) {
+            const uint32_t start = pre + incl - c;
+            ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);
+            tile_fill[t] = start;
+            if (c > (uint32_t)kSmallMax) big_list[atomicAdd(big_count, 1u)] = (uint32_t)t;
+        }
+        __syncthreads();
+        if (tid == 1023) s_carry = pre + incl;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kWalkBlock)
+tile_scatter_kernel(int P, int gx, int gy, int row0, int row1, const float4* __restrict__ rec,
+                    const int* __restrict__ radii, const uint32_t* __restrict__ offsets,
+                    uint32_t* __restrict__ tile_fill, unsigned long long* __restrict__ pairs) {
+    walk_instances(P, gx, gy, row0, row1, rec, radii, offsets,
+                   [&](uint32_t tile, uint32_t dbits, uint32_t idx) {
+                       const uint32_t slot = atomicAdd(tile_fill + tile, 1u);
+                       pairs[slot] = ((unsigned long long)dbits << 32) | idx;
+                   });
+}
+
+// Bitonic sorting network in its all-ascending form: each merge of block size k starts with a
+// "flip" step (i <-> mirror of i inside the block) followed by the usual half-cleaners j = k/4..1.
+// Every compare-exchange moves the smaller key to the lower index, so elements beyond n can be
+// treated as +inf without ever being touched: m is just the next power of two >= n.
+// pair_of(): the t-th pair (i < l) of a step.
+template <typename I>
+__device__ __forceinline__ void flip_pair(I t, I k, int lg_half, I& i, I& l) {
+    const I half = k >> 1, blk = t >> lg_half, o = t & (half - 1);
+    i = blk * k + o;
+    l = blk * k + (k - 1 - o);
+}
+template <typename I>
+__device__ __forceinline__ void half_pair(I t, I j, I& i, I& l) {
+    i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+    l = i | j;
+}
+
+template <int T, typename I, typename Ptr>
+__device__ __forceinline__ void bitonic_ascending(Ptr s, I n, I m, int tid) {
+    int lg_half = 0;
+    for (I k = 2; k <= m; k <<= 1, lg_half++) {
+        for (I t = tid; t < (m >> 1); t += T) {
+            I i, l;
+            flip_pair<I>(t, k, lg_half, i, l);
+            if (l < n) {
+                const unsigned long long a = s[i], b = s[l];
+                if (a > b) { s[i] = b; s[l] = a; }
+            }
+        }
+        __syncthreads();
+        for (I j = k >> 2; j > 0; j >>= 1) {
+            for (I t = tid; t < (m >> 1); t += T) {
+                I i, l;
+                half_pair<I>(t, j, i, l);
+                if (l < n) {
+                    const unsigned long long a = s[i], b = s[l];
+                    if (a > b) { s[i] = b; s[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ __forceinline__ int next_pow2(int n) {
+    return n <= 32 ? 32 : 1 << (32 - __clz(n - 1));
+}
+
+template <int T>
+__device__ __forceinline__ void sort_tile_in_smem(unsigned long long* s, uint32_t tile, uint2 rg,
+                                                  const unsigned long long* __restrict__ pairs,
+                                                  uint32_t* __restrict__ point_list,
+                                                  unsigned long long* __restrict__ keys_sorted, int tid) {
+    const int n = (int)(rg.y - rg.x);
+    const int m = next_pow2(n);
+    for (int i = tid; i < n; i += T) s[i] = pairs[rg.x + i];
+    __syncthreads();
+    bitonic_ascending<T, int>(s, n, m, tid);
+    for (int i = tid; i < n; i += T) {
+        const unsigned long long v = s[i];
+        point_list[rg.x + i] = (uint32_t)v;
+        if (keys_sorted) keys_sorted[rg.x + i] = ((unsigned long long)tile << 32) | (v >> 32);
+    }
+}
+
+__global__ void __launch_bounds__(128)
+tile_sort_small_kernel(const uint2* __restrict__ ranges, const unsigned long long* __restrict__ pairs,
+                       uint32_t* __restrict__ point_list, unsigned long long* __restrict__ keys_sorted) {
+    __shared__ unsigned long long s[kSmallMax];
+    const uint32_t tile = blockIdx.x;
+    const uint2 rg = ranges[tile];
+    const int n = (int)(rg.y - rg.x);
+    if (n == 0 || n > kSmallMax) return;
+    if (n == 1) {
+        if (threadIdx.x == 0) {
+            const unsigned long long v = pairs[rg.x];
+            point_list[rg.x] = (uint32_t)v;
+            if (keys_sorted) keys_sorted[rg.x] = ((unsigned long long)tile << 32) | (v >> 32);
+        }
+        return;
+    }
+    sort_tile_in_smem<128>(s, tile, rg, pairs, point_list, keys_sorted, threadIdx.x);
+}
+
+// Tiles with more than kSmallMax entries: persistent CTAs walk the big-tile list.
+__global__ void __launch_bounds__(1024)
+tile_sort_large_kernel(const uint2* __restrict__ ranges, unsigned long long* __restrict__ pairs,
+                       uint32_t* __restrict__ point_list, unsigned long long* __restrict__ keys_sorted,
+                       const uint32_t* __restrict__ big_list, const uint32_t* __restrict__ big_count) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned long long* s = reinterpret_cast<unsigned long long*>(smem_raw);
+    const uint32_t nb = *big_count;
+    const int tid = threadIdx.x;
+    for (uint32_t b = blockIdx.x; b < nb; b += gridDim.x) {
+        const uint32_t tile = big_list[b];
+        const uint2 rg = ranges[tile];
+        const int n = (int)(rg.y - rg.x);
+        if (n <= kLargeMax) {
+            sort_tile_in_smem<1024>(s, tile, rg, pairs, point_list, keys_sorted, tid);
+            __syncthreads();
+        } else {
+            // global-memory bitonic (same all-ascending network, virtual +inf beyond n)
+            unsigned long long* g = pairs + rg.x;
+            const long long m = 1ll << (64 - __clzll((long long)n - 1));
+            bitonic_ascending<1024, long long>(g, (long long)n, m, tid);
+            for (int i = tid; i < n; i += 1024) {
+                const unsigned long long v = g[i];
+                point_list[rg.x + i] = (uint32_t)v;
+                if (keys_sorted) keys_sorted[rg.x + i] = ((unsigned long long)tile << 32) | (v >> 32);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+size_t bucket_temp_bytes(int tiles) { return align_up((size_t)tiles * 4, 256) * 3 + 256; }
+
+int launch_bucket_binning(int P, size_t R, int gx, int gy, int row0, int row1, const float4* rec,
+                          const int* radii, const uint32_t* offsets, unsigned long long* pairs,
+                          uint32_t* point_list, unsigned long long* keys_sorted, uint2* ranges,
+                          void* temp, cudaStream_t stream) {
+    const int tiles = gx * gy;
+    char* c = (char*)temp;
+    const size_t stride = align_up((size_t)tiles * 4, 256);
+    uint32_t* tile_count = (uint32_t*)c;
+    uint32_t* tile_fill = (uint32_t*)(c + stride);
+    uint32_t* big_list = (uint32_t*)(c + 2 * stride);
+    uint32_t* big_count = (uint32_t*)(c + 3 * stride);
+    SURFEL_CUDA_OK(cudaMemsetAsync(tile_count, 0, (size_t)tiles * 4, stream));
+    const int blocks = (P + kWalkBlock - 1) / kWalkBlock;
+    if (P > 0 && R > 0) {
+        LaunchScope scope(kStDuplicate, stream);
+        tile_count_kernel<<<blocks, kWalkBlock, 0, stream>>>(P, gx, gy, row0, row1, rec, radii, offsets, tile_count);
+        SURFEL_CUDA_OK(cudaGetLastError());
+    }
+    {
+        LaunchScope scope(kStRanges, stream);
+        tile_scan_kernel<<<1, 1024, 0, stream>>>(tiles, tile_count, ranges, tile_fill, big_list, big_count);
+        SURFEL_CUDA_OK(cudaGetLastError());
+    }
+    if (P <= 0 || R == 0) return 0;
+    {
+        LaunchScope scope(kStDuplicate, stream);
+        tile_scatter_kernel<<<blocks, kWalkBlock, 0, stream>>>(P, gx, gy, row0, row1, rec, radii, offsets, tile_fill, pairs);
+        SURFEL_CUDA_OK(cudaGetLastError());
+    }
+    {
+        LaunchScope scope(kStSortPass, stream);
+        tile_sort_small_kernel<<<tiles, 128, 0, stream>>>(ranges, pairs, point_list, keys_sorted);
+        SURFEL_CUDA_OK(cudaGetLastError());
+    }
+    {
+        static bool attr_set = false;
+        if (!attr_set) {
+            SURFEL_CUDA_OK(cudaFuncSetAttribute(tile_sort_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                kLargeMax * 8));
+            attr_set = true;
+        }
+        LaunchScope scope(kStSortPass, stream);
+        tile_sort_large_kernel<<<148, 1024, kLargeMax * 8, stream>>>(ranges, pairs, point_list, keys_sorted, big_list, big_count);
+        SURFEL_CUDA_OK(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // namespace surfel

@@ -65,6 +65,15 @@ int launch_radix_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b
                             uint32_t* vals_b, size_t n, int end_bit, void* temp,
                             cudaStream_t stream);
 
+// Tile-bucketed binning (bucket_sort.cu): counting scatter by tile + per-tile shared-memory sort.
+// Produces ranges + point_list (+ keys_sorted if non-NULL) identical to duplicate -> stable radix
+// sort -> identifyTileRanges.  `pairs` is an R x u64 scratch buffer.
+size_t bucket_temp_bytes(int tiles);
+int launch_bucket_binning(int P, size_t R, int gx, int gy, int row0, int row1, const float4* rec,
+                          const int* radii, const uint32_t* offsets, unsigned long long* pairs,
+                          uint32_t* point_list, unsigned long long* keys_sorted, uint2* ranges,
+                          void* temp, cudaStream_t stream);
+
 int launch_render_fwd(const RenderParams& p, cudaStream_t stream);
 int launch_render_bwd(const RenderParams& p, cudaStream_t stream);
 

@@ -39,6 +39,7 @@ SIGNATURES = {
     "surfel_forward_render": (c_int, [ctypes.POINTER(SurfelSettings), c_int, c_uint32] + [c_void_p] * 6 + [c_void_p]),
     "surfel_bin_duplicate": (c_int, [ctypes.POINTER(SurfelSettings), c_int, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "surfel_bin_sort": (c_int, [ctypes.POINTER(SurfelSettings), c_uint32, c_void_p, c_void_p]),
+    "surfel_bin_bucket": (c_int, [ctypes.POINTER(SurfelSettings), c_int, c_uint32, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "surfel_render_forward": (c_int, [ctypes.POINTER(SurfelSettings), c_uint32] + [c_void_p] * 5 + [c_void_p]),
     "surfel_backward": (c_int, [ctypes.POINTER(SurfelSettings), c_int, c_int, c_uint32] + [c_void_p] * 5 + [c_int]
                         + [c_void_p] * 15 + [c_int, c_void_p]),

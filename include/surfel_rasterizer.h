@@ -105,6 +105,12 @@ int surfel_forward_render(const surfel_settings_t* s, int P, uint32_t R, const i
 int surfel_bin_duplicate(const surfel_settings_t* s, int P, uint32_t R, const void* geom_ws,
                          const int32_t* radii, void* binning_ws, void* stream);
 int surfel_bin_sort(const surfel_settings_t* s, uint32_t R, void* binning_ws, void* stream);
+/* Production binning used by surfel_forward_render: counting scatter of (depth|idx) pairs into tile
+ * buckets + per-tile shared-memory sort; fills ranges and the point list (vals_sorted), and the
+ * sorted keys too when write_keys != 0.  Result is identical to surfel_bin_duplicate + surfel_bin_sort
+ * (the CUB-free device-wide radix sort), which stays selectable with SURFEL_SORT=radix. */
+int surfel_bin_bucket(const surfel_settings_t* s, int P, uint32_t R, const void* geom_ws,
+                      const int32_t* radii, void* binning_ws, int write_keys, void* stream);
 int surfel_render_forward(const surfel_settings_t* s, uint32_t R, const void* geom_ws,
                           const void* binning_ws, void* image_ws, float* out_color,
                           float* out_others, void* stream);

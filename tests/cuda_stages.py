@@ -78,6 +78,20 @@ class CudaPipeline:
         return dict(keys_unsorted=b[o[0]:o[0] + 8 * R].view(np.uint64).copy(),
                     vals_unsorted=b[o[1]:o[1] + 4 * R].view(np.uint32).copy())
 
+    def bucket(self):
+        """Production binning path (tile buckets + per-tile sort); same outputs as duplicate()+sort()."""
+        lib = self.lib
+        self.binning = torch.zeros(lib.surfel_binning_bytes(self.R, self.W, self.H), dtype=torch.uint8, device="cuda")
+        _cabi.check(lib.surfel_bin_bucket(ctypes.byref(self.cs), self.P, self.R, self.geom.data_ptr(),
+                                          self.radii.data_ptr(), self.binning.data_ptr(), 1, self.stream))
+        torch.cuda.synchronize()
+        o = self._bin_views()
+        b = self.binning.cpu().numpy()
+        R, tiles = self.R, self.gx * self.gy
+        return dict(keys_sorted=b[o[2]:o[2] + 8 * R].view(np.uint64).copy(),
+                    vals_sorted=b[o[3]:o[3] + 4 * R].view(np.uint32).copy(),
+                    ranges=b[o[4]:o[4] + 8 * tiles].view(np.uint32).reshape(tiles, 2).copy())
+
     def sort(self):
         _cabi.check(self.lib.surfel_bin_sort(ctypes.byref(self.cs), self.R, self.binning.data_ptr(), self.stream))
         torch.cuda.synchronize()

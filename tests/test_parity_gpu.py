@@ -81,6 +81,41 @@ def test_preprocess_and_binning_bitexact(oracle, cuda_lib, case, sh_degree):
     np.testing.assert_array_equal(srt["keys_sorted"], binned["keys_sorted"])
     np.testing.assert_array_equal(srt["vals_sorted"], binned["vals_sorted"])
     np.testing.assert_array_equal(srt["ranges"], binned["ranges"])
+    # production binning path (tile buckets + per-tile sort) gives the identical result
+    bkt = pipe.bucket()
+    np.testing.assert_array_equal(bkt["keys_sorted"], binned["keys_sorted"])
+    np.testing.assert_array_equal(bkt["vals_sorted"], binned["vals_sorted"])
+    np.testing.assert_array_equal(bkt["ranges"], binned["ranges"])
+
+
+@pytest.mark.parametrize("per_tile", [3000, 20000])
+def test_bucket_sort_crowded_tiles(oracle, cuda_lib, per_tile):
+    """Thousands of splats piled onto a few tiles: exercises the large-tile (shared memory, 1024
+    threads) and the global-memory fallback of the per-tile sort, plus equal-depth ties."""
+    from cuda_stages import CudaPipeline
+    W = H = 64
+    cam = S.to_numpy(S.make_camera(W, H))
+    rng = np.random.default_rng(per_tile)
+    P = per_tile
+    z = rng.uniform(3.0, 3.5, P).astype(np.float32)
+    z[: P // 4] = np.float32(3.25)                       # many exactly equal depths -> ties by index
+    xy = rng.normal(0, 0.01, (P, 2)).astype(np.float32)
+    scene = dict(means3D=np.concatenate([xy, z[:, None]], 1).astype(np.float32),
+                 scales=np.full((P, 2), 0.004, np.float32),
+                 rotations=np.tile(np.array([[1, 0, 0, 0]], np.float32), (P, 1)),
+                 opacities=np.full((P, 1), 0.01, np.float32),
+                 shs=rng.normal(0, 0.3, (P, 16, 3)).astype(np.float32))
+    bg = np.zeros(3, np.float32)
+    pre, binned, img = oracle.forward(scene, cam, bg)
+    assert (binned["ranges"][:, 1] - binned["ranges"][:, 0]).max() >= per_tile // 2
+    pipe = CudaPipeline(scene, cam, bg)
+    pipe.preprocess()
+    bkt = pipe.bucket()
+    np.testing.assert_array_equal(bkt["ranges"], binned["ranges"])
+    np.testing.assert_array_equal(bkt["keys_sorted"], binned["keys_sorted"])
+    np.testing.assert_array_equal(bkt["vals_sorted"], binned["vals_sorted"])
+    gi = pipe.render()
+    assert_close_budget("color", gi["color"], img["color"], budget=5e-3)
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -310,6 +345,10 @@ def test_full_resolution_properties(oracle, cuda_lib, name, P):
     np.testing.assert_array_equal(gp["radii"], pre["radii"])
     np.testing.assert_array_equal(gp["offsets"], binned["offsets"])
     pipe.duplicate(); srt = pipe.sort()
+    np.testing.assert_array_equal(srt["keys_sorted"], binned["keys_sorted"])
+    np.testing.assert_array_equal(srt["vals_sorted"], binned["vals_sorted"])
+    np.testing.assert_array_equal(srt["ranges"], binned["ranges"])
+    srt = pipe.bucket()                                   # production path, same bar
     np.testing.assert_array_equal(srt["keys_sorted"], binned["keys_sorted"])
     np.testing.assert_array_equal(srt["vals_sorted"], binned["vals_sorted"])
     np.testing.assert_array_equal(srt["ranges"], binned["ranges"])
