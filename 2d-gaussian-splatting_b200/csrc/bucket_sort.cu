@@ -84,7 +84,7 @@ tile_count_kernel(int P, int gx, int gy, int row0, int row1, const float4* __res
 
 // One block: exclusive scan of tile_count -> ranges; zero the fill cursors; collect big tiles.
 __global__ void __launch_bounds__(1024)
-tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
+tile_scan_kernel(int tiles, uint32_t cap, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
                  uint32_t* __restrict__ tile_fill, uint32_t* __restrict__ big_list,
                  uint32_t* __restrict__ big_count) {
     __shared__ uint32_t s_warp[32];
@@ -106,10 +106,15 @@ tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __re
         uint32_t pre = s_carry;
         for (int w = 0; w < warp; w++) pre += s_warp[w];
         if (t < tiles) {
-            const uint32_t start = pre + incl - c;
-            ranges[t] = c ? make_uint2(start, start + c) : make_uint2(0u, 0u);
-            tile_fill[t] = start;
-            if (c > (uint32_t)kSmallMax) big_list[atomicAdd(big_count, 1u)] = (uint32_t)t;
+            // `cap` = number of instance slots the caller allocated.  When the forward is launched
+            // speculatively with a capacity guess (no host sync on R) and the guess was too small,
+            // everything is clamped so that no kernel touches memory past the buffers; the host then
+            // sees R > cap and re-runs with exact sizes.
+            const uint32_t start = min(pre + incl - c, cap), end = min(pre + incl, cap);
+            const uint32_t cc = end - start;
+            ranges[t] = cc ? make_uint2(start, end) : make_uint2(0u, 0u);
+            tile_fill[t] = pre + incl - c;
+            if (cc > (uint32_t)kSmallMax) big_list[atomicAdd(big_count, 1u)] = (uint32_t)t;
         }
         __syncthreads();
         if (tid == 1023) s_carry = pre + incl;
@@ -120,11 +125,11 @@ tile_scan_kernel(int tiles, const uint32_t* __restrict__ tile_count, uint2* __re
 __global__ void __launch_bounds__(kWalkBlock)
 tile_scatter_kernel(int P, int gx, int gy, int row0, int row1, const float4* __restrict__ rec,
                     const int* __restrict__ radii, const uint32_t* __restrict__ offsets,
-                    uint32_t* __restrict__ tile_fill, unsigned long long* __restrict__ pairs) {
+                    uint32_t* __restrict__ tile_fill, unsigned long long* __restrict__ pairs, uint32_t cap) {
     walk_instances(P, gx, gy, row0, row1, rec, radii, offsets,
                    [&](uint32_t tile, uint32_t dbits, uint32_t idx) {
                        const uint32_t slot = atomicAdd(tile_fill + tile, 1u);
-                       pairs[slot] = ((unsigned long long)dbits << 32) | idx;
+                       if (slot < cap) pairs[slot] = ((unsigned long long)dbits << 32) | idx;
                    });
 }
 
@@ -259,23 +264,23 @@ int launch_bucket_binning(int P, size_t R, int gx, int gy, int row0, int row1, c
     SURFEL_CUDA_OK(cudaMemsetAsync(tile_count, 0, (size_t)tiles * 4, stream));
     const int blocks = (P + kWalkBlock - 1) / kWalkBlock;
     if (P > 0 && R > 0) {
-        LaunchScope scope(kStDuplicate, stream);
+        LaunchScope scope(kStTileCount, stream);
         tile_count_kernel<<<blocks, kWalkBlock, 0, stream>>>(P, gx, gy, row0, row1, rec, radii, offsets, tile_count);
         SURFEL_CUDA_OK(cudaGetLastError());
     }
     {
-        LaunchScope scope(kStRanges, stream);
-        tile_scan_kernel<<<1, 1024, 0, stream>>>(tiles, tile_count, ranges, tile_fill, big_list, big_count);
+        LaunchScope scope(kStTileScan, stream);
+        tile_scan_kernel<<<1, 1024, 0, stream>>>(tiles, (uint32_t)std::min<size_t>(R, 0xffffffffu), tile_count, ranges, tile_fill, big_list, big_count);
         SURFEL_CUDA_OK(cudaGetLastError());
     }
     if (P <= 0 || R == 0) return 0;
     {
-        LaunchScope scope(kStDuplicate, stream);
-        tile_scatter_kernel<<<blocks, kWalkBlock, 0, stream>>>(P, gx, gy, row0, row1, rec, radii, offsets, tile_fill, pairs);
+        LaunchScope scope(kStTileScatter, stream);
+        tile_scatter_kernel<<<blocks, kWalkBlock, 0, stream>>>(P, gx, gy, row0, row1, rec, radii, offsets, tile_fill, pairs, (uint32_t)std::min<size_t>(R, 0xffffffffu));
         SURFEL_CUDA_OK(cudaGetLastError());
     }
     {
-        LaunchScope scope(kStSortPass, stream);
+        LaunchScope scope(kStTileSort, stream);
         tile_sort_small_kernel<<<tiles, 128, 0, stream>>>(ranges, pairs, point_list, keys_sorted);
         SURFEL_CUDA_OK(cudaGetLastError());
     }
@@ -286,7 +291,7 @@ int launch_bucket_binning(int P, size_t R, int gx, int gy, int row0, int row1, c
                                                 kLargeMax * 8));
             attr_set = true;
         }
-        LaunchScope scope(kStSortPass, stream);
+        LaunchScope scope(kStTileSort, stream);
         tile_sort_large_kernel<<<148, 1024, kLargeMax * 8, stream>>>(ranges, pairs, point_list, keys_sorted, big_list, big_count);
         SURFEL_CUDA_OK(cudaGetLastError());
     }

@@ -6,7 +6,8 @@
 namespace surfel {
 
 enum Stage { kStPreFwd = 0, kStDuplicate, kStSortHist, kStSortPass, kStRanges, kStRenderFwd,
-             kStRenderBwd, kStPreBwd, kStMarkVisible, kNumStages };
+             kStRenderBwd, kStPreBwd, kStMarkVisible, kStTileCount, kStTileScan, kStTileScatter,
+             kStTileSort, kNumStages };
 
 void prof_count_launch();
 bool prof_enabled();

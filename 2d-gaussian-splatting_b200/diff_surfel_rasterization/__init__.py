@@ -95,13 +95,18 @@ def last_num_rendered():
 
 
 
+_capacity = {}
+# SURFEL_SPECULATIVE=0 restores upstream's launch order (block on R, then launch binning + render)
+_SPECULATIVE = bool(int(os.environ.get("SURFEL_SPECULATIVE", "1"))) and os.environ.get("SURFEL_SORT", "") != "radix"
+
+
 def _pinned_u32(device):
     key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    buf = _pinned_counter.get(key)
-    if buf is None:
-        buf = torch.zeros(1, dtype=torch.int32).pin_memory()
-        _pinned_counter[key] = buf
-    return buf
+    ent = _pinned_counter.get(key)
+    if ent is None:
+        ent = (torch.zeros(1, dtype=torch.int32).pin_memory(), torch.cuda.Event())
+        _pinned_counter[key] = ent
+    return ent
 
 
 class _RasterizeGaussians(torch.autograd.Function):
@@ -136,25 +141,42 @@ class _RasterizeGaussians(torch.autograd.Function):
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         geom = torch.empty((lib.surfel_geom_bytes(P),), dtype=torch.uint8, device=dev)
         img = torch.empty((lib.surfel_image_bytes(W, H),), dtype=torch.uint8, device=dev)
-        R = 0
+        R = cap = 0
         with torch.cuda.device(dev):
             if P > 0:
-                host_R = _pinned_u32(dev)
+                host_R, ev = _pinned_u32(dev)
                 _cabi.check(lib.surfel_forward_preprocess(
                     ctypes.byref(cs), P, M, _ptr(means3D), _ptr(opacities), _ptr(scales),
                     _ptr(rotations), _ptr(cov3Ds_precomp), _ptr(sh), _ptr(colors_precomp),
                     radii.data_ptr(), geom.data_ptr(), host_R.data_ptr(), stream))
-                # the one host<->device sync of the forward: R sizes the binning workspace
-                torch.cuda.current_stream(dev).synchronize()
+                ev.record(torch.cuda.current_stream(dev))
+                # The instance count R sizes the binning workspace, so upstream blocks here until the
+                # device has produced it.  We launch binning + render SPECULATIVELY with the capacity
+                # remembered from earlier calls of the same shape (every kernel clamps to it), and only
+                # then wait for R: the device keeps working while the host waits, and the wait ends as
+                # soon as preprocess is done.  A too-small guess costs one re-launch.
+                key = (dev.index, P, W, H, cs.tile_row_begin, cs.tile_row_end)
+                cap = _capacity.get(key, 0) if _SPECULATIVE else 0
+                if cap:
+                    binning = torch.empty((lib.surfel_binning_bytes(cap, W, H),), dtype=torch.uint8, device=dev)
+                    _cabi.check(lib.surfel_forward_render(
+                        ctypes.byref(cs), P, cap, radii.data_ptr(), geom.data_ptr(), binning.data_ptr(),
+                        img.data_ptr(), color.data_ptr(), allmap.data_ptr(), stream))
+                ev.synchronize()
                 R = int(host_R.item()) & 0xFFFFFFFF
-            binning = torch.empty((lib.surfel_binning_bytes(R, W, H),), dtype=torch.uint8, device=dev)
-            _cabi.check(lib.surfel_forward_render(
-                ctypes.byref(cs), P, R, radii.data_ptr(), geom.data_ptr(), binning.data_ptr(),
-                img.data_ptr(), color.data_ptr(), allmap.data_ptr(), stream))
+                if R > cap or not cap:
+                    cap = R if not _SPECULATIVE else int(R * 1.25) + 4096
+                    _capacity[key] = cap
+                    binning = None
+            if P == 0 or binning is None:
+                binning = torch.empty((lib.surfel_binning_bytes(cap, W, H),), dtype=torch.uint8, device=dev)
+                _cabi.check(lib.surfel_forward_render(
+                    ctypes.byref(cs), P, cap, radii.data_ptr(), geom.data_ptr(), binning.data_ptr(),
+                    img.data_ptr(), color.data_ptr(), allmap.data_ptr(), stream))
 
         _last["num_rendered"] = R
         ctx.raster_settings = rs
-        ctx.num_rendered = R
+        ctx.num_rendered = cap        # the workspace layout was carved for `cap` instance slots
         ctx.M = M
         ctx.flags = (sh is not None, colors_precomp is not None, scales is not None, cov3Ds_precomp is not None)
         none = torch.empty(0, device=dev)
