@@ -113,7 +113,7 @@ int surfel_image_offsets(int W, int H, size_t* out) {
 int surfel_forward_preprocess(const surfel_settings_t* s, int P, int M, const float* means3D,
                               const float* opacities, const float* scales, const float* rotations,
                               const float* transMat_precomp, const float* shs,
-                              const float* colors_precomp, int32_t* radii, void* geom_ws,
+                              const float* colors_precomp, int32_t* radii, void* geom_ws, void* image_ws,
                               uint32_t* num_rendered_host, void* stream) {
     Frame f;
     if (!frame_of(s, f)) return 1;
@@ -141,6 +141,7 @@ int surfel_forward_preprocess(const surfel_settings_t* s, int P, int M, const fl
     p.radii = radii; p.rec = (float4*)(g + L.rec); p.tiles_touched = (uint32_t*)(g + L.tiles_touched);
     p.offsets = (uint32_t*)(g + L.offsets); p.clamped = (uint8_t*)(g + L.clamped);
     p.scan_status = (unsigned long long*)(g + L.scan_status); p.counters = (uint32_t*)(g + L.counters);
+    p.tile_count = image_ws ? (uint32_t*)((char*)image_ws + image_layout(f.W, f.H).tile_count) : nullptr;
     if (launch_preprocess_fwd(p, st)) return 1;
     if (num_rendered_host)
         SURFEL_CUDA_OK(cudaMemcpyAsync(num_rendered_host, p.counters + 1, 4, cudaMemcpyDeviceToHost, st));
@@ -188,7 +189,8 @@ int surfel_render_forward(const surfel_settings_t* s, uint32_t R, const void* ge
 }
 
 int surfel_bin_bucket(const surfel_settings_t* s, int P, uint32_t R, const void* geom_ws,
-                      const int32_t* radii, void* binning_ws, int write_keys, void* stream) {
+                      const int32_t* radii, void* binning_ws, const void* image_ws_with_counts,
+                      int write_keys, void* stream) {
     Frame f;
     if (!frame_of(s, f)) return 1;
     GeomLayout L = geom_layout(P);
@@ -199,16 +201,18 @@ int surfel_bin_bucket(const surfel_settings_t* s, int P, uint32_t R, const void*
     return launch_bucket_binning(P, R, f.gx, f.gy, f.row0, f.row1, (const float4*)(g + L.rec), radii,
                                  (const uint32_t*)(g + L.offsets), pairs, v.v_sorted,
                                  write_keys ? (unsigned long long*)v.k_sorted : nullptr, v.ranges, v.temp,
+                                 image_ws_with_counts ? (const uint32_t*)((const char*)image_ws_with_counts +
+                                                                          image_layout(f.W, f.H).tile_count) : nullptr,
                                  (cudaStream_t)stream);
 }
 
 int surfel_forward_render(const surfel_settings_t* s, int P, uint32_t R, const int32_t* radii,
-                          const void* geom_ws, void* binning_ws, void* image_ws, float* out_color,
-                          float* out_others, void* stream) {
+                          const void* geom_ws, void* binning_ws, void* image_ws, int tile_counts_ready,
+                          float* out_color, float* out_others, void* stream) {
     // SURFEL_SORT=radix selects the device-wide onesweep radix sort instead of the tile-bucketed path
     static const bool use_radix = [] { const char* e = getenv("SURFEL_SORT"); return e && !strcmp(e, "radix"); }();
     if (!use_radix) {
-        if (surfel_bin_bucket(s, P, R, geom_ws, radii, binning_ws, 0, stream)) return 1;
+        if (surfel_bin_bucket(s, P, R, geom_ws, radii, binning_ws, tile_counts_ready ? image_ws : nullptr, 0, stream)) return 1;
         return surfel_render_forward(s, R, geom_ws, binning_ws, image_ws, out_color, out_others, stream);
     }
     if (surfel_bin_duplicate(s, P, R, geom_ws, radii, binning_ws, stream)) return 1;

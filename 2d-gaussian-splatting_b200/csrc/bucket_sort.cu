@@ -198,6 +198,87 @@ __device__ __forceinline__ void sort_tile_in_smem(unsigned long long* s, uint32_
     }
 }
 
+// ---- fast path for the common case (n <= 2048): 128 threads, E keys per thread in REGISTERS ----
+// Classic bitonic network on the blocked layout e = tid*E + r: strides below E are compare-exchanges
+// between registers of one thread, strides below 32*E are warp shuffles, only the few largest strides
+// go through shared memory.  ~3x fewer instructions than running every stage through shared memory.
+constexpr unsigned long long kPad = ~0ull;
+
+__device__ __forceinline__ void ce_regs(unsigned long long& a, unsigned long long& b, bool asc) {
+    const bool sw = (a > b) == asc;
+    const unsigned long long lo = sw ? b : a, hi = sw ? a : b;
+    a = lo; b = hi;
+}
+
+template <int E>
+__device__ __forceinline__ void block_bitonic_regs(unsigned long long (&v)[E], unsigned long long* smem, int tid) {
+    constexpr int T = 128, M = E * T;
+    // phase A: merges that fit inside one thread
+#pragma unroll
+    for (int k = 2; k <= E; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int r = 0; r < E; r++)
+                if ((r & j) == 0) ce_regs(v[r], v[r | j], (((tid * E) + r) & k) == 0);
+        }
+    }
+    // phase B: merges spanning threads
+    for (int k = 2 * E; k <= M; k <<= 1) {
+        const bool asc = ((tid * E) & k) == 0;        // r < E <= k/2 never reaches bit k
+        for (int j = k >> 1; j >= E; j >>= 1) {
+            const int jl = j / E;
+            const bool keep_min = ((tid & jl) == 0) == asc;
+            if (jl < 32) {
+#pragma unroll
+                for (int r = 0; r < E; r++) {
+                    const unsigned long long o = __shfl_xor_sync(0xffffffffu, v[r], jl);
+                    v[r] = keep_min ? (v[r] < o ? v[r] : o) : (v[r] > o ? v[r] : o);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < E; r++) smem[r * T + tid] = v[r];      // [r][tid]: conflict-free
+                __syncthreads();
+#pragma unroll
+                for (int r = 0; r < E; r++) {
+                    const unsigned long long o = smem[r * T + (tid ^ jl)];
+                    v[r] = keep_min ? (v[r] < o ? v[r] : o) : (v[r] > o ? v[r] : o);
+                }
+                __syncthreads();
+            }
+        }
+#pragma unroll
+        for (int j = E >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int r = 0; r < E; r++)
+                if ((r & j) == 0) ce_regs(v[r], v[r | j], asc);
+        }
+    }
+}
+
+template <int E>
+__device__ __forceinline__ void sort_tile_regs(unsigned long long* smem, uint32_t tile, uint2 rg,
+                                               const unsigned long long* __restrict__ pairs,
+                                               uint32_t* __restrict__ point_list,
+                                               unsigned long long* __restrict__ keys_sorted, int tid) {
+    const int n = (int)(rg.y - rg.x);
+    unsigned long long v[E];
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+        const int e = tid * E + r;
+        v[r] = e < n ? pairs[rg.x + e] : kPad;
+    }
+    block_bitonic_regs<E>(v, smem, tid);
+#pragma unroll
+    for (int r = 0; r < E; r++) {
+        const int e = tid * E + r;
+        if (e < n) {
+            point_list[rg.x + e] = (uint32_t)v[r];
+            if (keys_sorted) keys_sorted[rg.x + e] = ((unsigned long long)tile << 32) | (v[r] >> 32);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128)
 tile_sort_small_kernel(const uint2* __restrict__ ranges, const unsigned long long* __restrict__ pairs,
                        uint32_t* __restrict__ point_list, unsigned long long* __restrict__ keys_sorted) {
@@ -206,15 +287,12 @@ tile_sort_small_kernel(const uint2* __restrict__ ranges, const unsigned long lon
     const uint2 rg = ranges[tile];
     const int n = (int)(rg.y - rg.x);
     if (n == 0 || n > kSmallMax) return;
-    if (n == 1) {
-        if (threadIdx.x == 0) {
-            const unsigned long long v = pairs[rg.x];
-            point_list[rg.x] = (uint32_t)v;
-            if (keys_sorted) keys_sorted[rg.x] = ((unsigned long long)tile << 32) | (v >> 32);
-        }
-        return;
-    }
-    sort_tile_in_smem<128>(s, tile, rg, pairs, point_list, keys_sorted, threadIdx.x);
+    const int tid = threadIdx.x;
+    if (n <= 128)       sort_tile_regs<1>(s, tile, rg, pairs, point_list, keys_sorted, tid);
+    else if (n <= 256)  sort_tile_regs<2>(s, tile, rg, pairs, point_list, keys_sorted, tid);
+    else if (n <= 512)  sort_tile_regs<4>(s, tile, rg, pairs, point_list, keys_sorted, tid);
+    else if (n <= 1024) sort_tile_regs<8>(s, tile, rg, pairs, point_list, keys_sorted, tid);
+    else                sort_tile_regs<16>(s, tile, rg, pairs, point_list, keys_sorted, tid);
 }
 
 // Tiles with more than kSmallMax entries: persistent CTAs walk the big-tile list.
@@ -253,7 +331,7 @@ size_t bucket_temp_bytes(int tiles) { return align_up((size_t)tiles * 4, 256) * 
 int launch_bucket_binning(int P, size_t R, int gx, int gy, int row0, int row1, const float4* rec,
                           const int* radii, const uint32_t* offsets, unsigned long long* pairs,
                           uint32_t* point_list, unsigned long long* keys_sorted, uint2* ranges,
-                          void* temp, cudaStream_t stream) {
+                          void* temp, const uint32_t* tile_count_ready, cudaStream_t stream) {
     const int tiles = gx * gy;
     char* c = (char*)temp;
     const size_t stride = align_up((size_t)tiles * 4, 256);
@@ -261,9 +339,13 @@ int launch_bucket_binning(int P, size_t R, int gx, int gy, int row0, int row1, c
     uint32_t* tile_fill = (uint32_t*)(c + stride);
     uint32_t* big_list = (uint32_t*)(c + 2 * stride);
     uint32_t* big_count = (uint32_t*)(c + 3 * stride);
-    SURFEL_CUDA_OK(cudaMemsetAsync(tile_count, 0, (size_t)tiles * 4, stream));
     const int blocks = (P + kWalkBlock - 1) / kWalkBlock;
-    if (P > 0 && R > 0) {
+    if (tile_count_ready) {
+        tile_count = const_cast<uint32_t*>(tile_count_ready);   // counted by preprocess_fwd (fused)
+    } else {
+        SURFEL_CUDA_OK(cudaMemsetAsync(tile_count, 0, (size_t)tiles * 4, stream));
+    }
+    if (!tile_count_ready && P > 0 && R > 0) {
         LaunchScope scope(kStTileCount, stream);
         tile_count_kernel<<<blocks, kWalkBlock, 0, stream>>>(P, gx, gy, row0, row1, rec, radii, offsets, tile_count);
         SURFEL_CUDA_OK(cudaGetLastError());

@@ -44,7 +44,7 @@ struct GeomLayout {
     size_t rec, tiles_touched, offsets, clamped, scan_status, counters, total;
 };
 struct ImageLayout {
-    size_t accum, n_contrib, total;  // accum: final_T, M1, M2 planes; n_contrib: last, median
+    size_t accum, n_contrib, tile_count, total;  // accum: final_T, M1, M2; n_contrib: last, median; per-tile instance counts
 };
 struct BinningLayout {
     size_t keys_a, keys_b, vals_a, vals_b, ranges, sort_temp, total;
@@ -73,6 +73,8 @@ inline ImageLayout image_layout(int W, int H) {
     size_t o = 0;
     L.accum = o;      o = align_up(o + n * 3 * 4, 256);
     L.n_contrib = o;  o = align_up(o + n * 2 * 4, 256);
+    const size_t tiles = (size_t)((W + kBlockX - 1) / kBlockX) * (size_t)((H + kBlockY - 1) / kBlockY);
+    L.tile_count = o; o = align_up(o + tiles * 4, 256);
     L.total = o;
     return L;
 }

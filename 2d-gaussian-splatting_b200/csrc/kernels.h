@@ -14,6 +14,7 @@ struct PreFwdParams {
     const float* viewmatrix; const float* projmatrix; const float* campos;
     int* radii; float4* rec; uint32_t* tiles_touched; uint32_t* offsets; uint8_t* clamped;
     unsigned long long* scan_status; uint32_t* counters;
+    uint32_t* tile_count;   // optional (tiles): per-tile instance counts accumulated here (fused count)
 };
 
 struct PreBwdParams {
@@ -72,7 +73,7 @@ size_t bucket_temp_bytes(int tiles);
 int launch_bucket_binning(int P, size_t R, int gx, int gy, int row0, int row1, const float4* rec,
                           const int* radii, const uint32_t* offsets, unsigned long long* pairs,
                           uint32_t* point_list, unsigned long long* keys_sorted, uint2* ranges,
-                          void* temp, cudaStream_t stream);
+                          void* temp, const uint32_t* tile_count_ready, cudaStream_t stream);
 
 int launch_render_fwd(const RenderParams& p, cudaStream_t stream);
 int launch_render_bwd(const RenderParams& p, cudaStream_t stream);

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(kPreBlock, 6) preprocess_fwd_kernel(PreFwdPara
 
     bool visible = false;
     uint32_t tt = 0;
+    int rx0 = 0, ry0 = 0, rw = 1;
     float tm[9], nrm[3] = {0, 0, 0}, cx = 0, cy = 0, pvz = 0, opa = 0;
     int radius_i = 0;
     float px = 0, py = 0, pz = 0;
@@ -157,11 +158,34 @@ __global__ void __launch_bounds__(kPreBlock, 6) preprocess_fwd_kernel(PreFwdPara
                         get_rect(cx, cy, radius_i, p.gx, p.gy, p.row0, p.row1, x0, y0, x1, y1);
                         tt = (uint32_t)((x1 - x0) * (y1 - y0));
                         visible = tt != 0;
+                        rx0 = x0; ry0 = y0; rw = max(1, x1 - x0);
                     }
                 }
             }
         }
         if (visible) opa = p.opacities[idx];
+    }
+
+    // ---- fused per-tile instance count for the tile-bucketed binning (bucket_sort.cu): small rects
+    // are counted by their own thread, large ones are spread over the warp ----
+    if (p.tile_count != nullptr) {
+        if (visible && tt <= 8u) {
+            for (uint32_t i = 0; i < tt; i++) {
+                const uint32_t ry = i / (uint32_t)rw, rx = i - ry * (uint32_t)rw;
+                atomicAdd(p.tile_count + (uint32_t)(ry0 + (int)ry) * (uint32_t)p.gx + (uint32_t)(rx0 + (int)rx), 1u);
+            }
+        }
+        unsigned big = __ballot_sync(0xffffffffu, visible && tt > 8u);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const int bx0 = __shfl_sync(0xffffffffu, rx0, src), by0 = __shfl_sync(0xffffffffu, ry0, src);
+            const uint32_t bw = (uint32_t)__shfl_sync(0xffffffffu, rw, src), bt = __shfl_sync(0xffffffffu, tt, src);
+            for (uint32_t i = lane; i < bt; i += 32) {
+                const uint32_t ry = i / bw, rx = i - ry * bw;
+                atomicAdd(p.tile_count + (uint32_t)(by0 + (int)ry) * (uint32_t)p.gx + (uint32_t)(bx0 + (int)rx), 1u);
+            }
+        }
     }
 
     // ---- block inclusive scan of tiles_touched; the block aggregate is published NOW, before the
@@ -354,6 +378,7 @@ int launch_preprocess_fwd(const PreFwdParams& p, cudaStream_t stream) {
     const int blocks = (p.P + kPreBlock - 1) / kPreBlock;
     SURFEL_CUDA_OK(cudaMemsetAsync(p.scan_status, 0, (size_t)(blocks + 1) * 8, stream));
     SURFEL_CUDA_OK(cudaMemsetAsync(p.counters, 0, 64, stream));
+    if (p.tile_count) SURFEL_CUDA_OK(cudaMemsetAsync(p.tile_count, 0, (size_t)p.gx * p.gy * 4, stream));
     const bool vec4 = p.colors_precomp == nullptr && p.D <= 3 && p.M == 16 &&
                       (reinterpret_cast<uintptr_t>(p.shs) % 16 == 0);
     LaunchScope scope(kStPreFwd, stream);

@@ -148,7 +148,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _cabi.check(lib.surfel_forward_preprocess(
                     ctypes.byref(cs), P, M, _ptr(means3D), _ptr(opacities), _ptr(scales),
                     _ptr(rotations), _ptr(cov3Ds_precomp), _ptr(sh), _ptr(colors_precomp),
-                    radii.data_ptr(), geom.data_ptr(), host_R.data_ptr(), stream))
+                    radii.data_ptr(), geom.data_ptr(), img.data_ptr(), host_R.data_ptr(), stream))
                 ev.record(torch.cuda.current_stream(dev))
                 # The instance count R sizes the binning workspace, so upstream blocks here until the
                 # device has produced it.  We launch binning + render SPECULATIVELY with the capacity
@@ -161,7 +161,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                     binning = torch.empty((lib.surfel_binning_bytes(cap, W, H),), dtype=torch.uint8, device=dev)
                     _cabi.check(lib.surfel_forward_render(
                         ctypes.byref(cs), P, cap, radii.data_ptr(), geom.data_ptr(), binning.data_ptr(),
-                        img.data_ptr(), color.data_ptr(), allmap.data_ptr(), stream))
+                        img.data_ptr(), 1, color.data_ptr(), allmap.data_ptr(), stream))
                 ev.synchronize()
                 R = int(host_R.item()) & 0xFFFFFFFF
                 if R > cap or not cap:
@@ -172,7 +172,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 binning = torch.empty((lib.surfel_binning_bytes(cap, W, H),), dtype=torch.uint8, device=dev)
                 _cabi.check(lib.surfel_forward_render(
                     ctypes.byref(cs), P, cap, radii.data_ptr(), geom.data_ptr(), binning.data_ptr(),
-                    img.data_ptr(), color.data_ptr(), allmap.data_ptr(), stream))
+                    img.data_ptr(), int(P > 0), color.data_ptr(), allmap.data_ptr(), stream))
 
         _last["num_rendered"] = R
         ctx.raster_settings = rs

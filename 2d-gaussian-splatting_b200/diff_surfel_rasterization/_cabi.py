@@ -35,11 +35,11 @@ SIGNATURES = {
     "surfel_geom_offsets": (c_int, [c_int, ctypes.POINTER(c_size_t)]),
     "surfel_binning_offsets": (c_int, [c_size_t, c_int, c_int, ctypes.POINTER(c_size_t)]),
     "surfel_image_offsets": (c_int, [c_int, c_int, ctypes.POINTER(c_size_t)]),
-    "surfel_forward_preprocess": (c_int, [ctypes.POINTER(SurfelSettings), c_int, c_int] + [c_void_p] * 10 + [c_void_p]),
-    "surfel_forward_render": (c_int, [ctypes.POINTER(SurfelSettings), c_int, c_uint32] + [c_void_p] * 6 + [c_void_p]),
+    "surfel_forward_preprocess": (c_int, [ctypes.POINTER(SurfelSettings), c_int, c_int] + [c_void_p] * 11 + [c_void_p]),
+    "surfel_forward_render": (c_int, [ctypes.POINTER(SurfelSettings), c_int, c_uint32] + [c_void_p] * 4 + [c_int, c_void_p, c_void_p, c_void_p]),
     "surfel_bin_duplicate": (c_int, [ctypes.POINTER(SurfelSettings), c_int, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "surfel_bin_sort": (c_int, [ctypes.POINTER(SurfelSettings), c_uint32, c_void_p, c_void_p]),
-    "surfel_bin_bucket": (c_int, [ctypes.POINTER(SurfelSettings), c_int, c_uint32, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "surfel_bin_bucket": (c_int, [ctypes.POINTER(SurfelSettings), c_int, c_uint32, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "surfel_render_forward": (c_int, [ctypes.POINTER(SurfelSettings), c_uint32] + [c_void_p] * 5 + [c_void_p]),
     "surfel_backward": (c_int, [ctypes.POINTER(SurfelSettings), c_int, c_int, c_uint32] + [c_void_p] * 5 + [c_int]
                         + [c_void_p] * 15 + [c_int, c_void_p]),

@@ -85,21 +85,22 @@ int surfel_binning_offsets(size_t R, int W, int H, size_t* out5);
 int surfel_image_offsets(int W, int H, size_t* out2);
 
 /* Forward, stage 1: preprocess every splat and scan tiles_touched.  Writes radii (P) int32 and the
- * geometry workspace.  The instance count R is left in the workspace and, if
+ * geometry workspace.  If image_ws != NULL the per-tile instance counts are accumulated there in the
+ * same launch (fused count for the tile-bucketed binning; pass tile_counts_ready = 1 downstream).  The instance count R is left in the workspace and, if
  * num_rendered_host != NULL (pinned host memory), copied there asynchronously on `stream`; the
  * caller synchronises the stream (or an event) before reading it to size the binning workspace. */
 int surfel_forward_preprocess(const surfel_settings_t* s, int P, int M, const float* means3D,
                               const float* opacities, const float* scales, const float* rotations,
                               const float* transMat_precomp, const float* shs,
-                              const float* colors_precomp, int32_t* radii, void* geom_ws,
+                              const float* colors_precomp, int32_t* radii, void* geom_ws, void* image_ws,
                               uint32_t* num_rendered_host, void* stream);
 
 /* Forward, stage 2: emit keys, sort, find tile ranges, blend.  out_color (3,H,W), out_others
  * (7,H,W): 0 = sum w*depth, 1 = alpha, 2-4 = view-space normal, 5 = median depth, 6 = distortion
  * (channel order consumed at /root/reference/gaussian_renderer/__init__.py:118-135). */
 int surfel_forward_render(const surfel_settings_t* s, int P, uint32_t R, const int32_t* radii,
-                          const void* geom_ws, void* binning_ws, void* image_ws, float* out_color,
-                          float* out_others, void* stream);
+                          const void* geom_ws, void* binning_ws, void* image_ws, int tile_counts_ready,
+                          float* out_color, float* out_others, void* stream);
 
 /* The two halves of stage 2, exposed separately for parity tests. */
 int surfel_bin_duplicate(const surfel_settings_t* s, int P, uint32_t R, const void* geom_ws,
@@ -110,7 +111,8 @@ int surfel_bin_sort(const surfel_settings_t* s, uint32_t R, void* binning_ws, vo
  * sorted keys too when write_keys != 0.  Result is identical to surfel_bin_duplicate + surfel_bin_sort
  * (the CUB-free device-wide radix sort), which stays selectable with SURFEL_SORT=radix. */
 int surfel_bin_bucket(const surfel_settings_t* s, int P, uint32_t R, const void* geom_ws,
-                      const int32_t* radii, void* binning_ws, int write_keys, void* stream);
+                      const int32_t* radii, void* binning_ws, const void* image_ws_with_counts,
+                      int write_keys, void* stream);
 int surfel_render_forward(const surfel_settings_t* s, uint32_t R, const void* geom_ws,
                           const void* binning_ws, void* image_ws, float* out_color,
                           float* out_others, void* stream);

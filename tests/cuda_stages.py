@@ -17,7 +17,8 @@ def _p(t):
 
 
 class CudaPipeline:
-    def __init__(self, scene, cam, bg, sh_degree=3, scale_modifier=1.0, tile_rows=(0, 0)):
+    def __init__(self, scene, cam, bg, sh_degree=3, scale_modifier=1.0, tile_rows=(0, 0), fused_count=True):
+        self.fused_count = fused_count
         self.lib = _cabi.load()
         self.W, self.H = cam["W"], cam["H"]
         self.gx, self.gy = (self.W + 15) // 16, (self.H + 15) // 16
@@ -38,11 +39,13 @@ class CudaPipeline:
         lib, P = self.lib, self.P
         self.radii = torch.empty(P, dtype=torch.int32, device="cuda")
         self.geom = torch.zeros(lib.surfel_geom_bytes(P), dtype=torch.uint8, device="cuda")
+        self.img = torch.zeros(lib.surfel_image_bytes(self.W, self.H), dtype=torch.uint8, device="cuda")
         host_R = torch.zeros(1, dtype=torch.int32).pin_memory()
         _cabi.check(lib.surfel_forward_preprocess(
             ctypes.byref(self.cs), P, self.M, _p(self.means3D), _p(self.opacities), _p(self.scales),
             _p(self.rotations), _p(self.transMat_precomp), _p(self.shs), _p(self.colors_precomp),
-            self.radii.data_ptr(), self.geom.data_ptr(), host_R.data_ptr(), self.stream))
+            self.radii.data_ptr(), self.geom.data_ptr(), self.img.data_ptr() if self.fused_count else None,
+            host_R.data_ptr(), self.stream))
         torch.cuda.synchronize()
         self.R = int(host_R.item()) & 0xFFFFFFFF
         offs = (ctypes.c_size_t * 5)()
@@ -83,7 +86,8 @@ class CudaPipeline:
         lib = self.lib
         self.binning = torch.zeros(lib.surfel_binning_bytes(self.R, self.W, self.H), dtype=torch.uint8, device="cuda")
         _cabi.check(lib.surfel_bin_bucket(ctypes.byref(self.cs), self.P, self.R, self.geom.data_ptr(),
-                                          self.radii.data_ptr(), self.binning.data_ptr(), 1, self.stream))
+                                          self.radii.data_ptr(), self.binning.data_ptr(),
+                                          self.img.data_ptr() if self.fused_count else None, 1, self.stream))
         torch.cuda.synchronize()
         o = self._bin_views()
         b = self.binning.cpu().numpy()
@@ -104,7 +108,6 @@ class CudaPipeline:
 
     def render(self):
         lib, W, H = self.lib, self.W, self.H
-        self.img = torch.zeros(lib.surfel_image_bytes(W, H), dtype=torch.uint8, device="cuda")
         self.color = torch.zeros(3, H, W, device="cuda"); self.others = torch.zeros(7, H, W, device="cuda")
         _cabi.check(lib.surfel_render_forward(ctypes.byref(self.cs), self.R, self.geom.data_ptr(),
                                               self.binning.data_ptr(), self.img.data_ptr(),

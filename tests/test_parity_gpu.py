@@ -86,6 +86,13 @@ def test_preprocess_and_binning_bitexact(oracle, cuda_lib, case, sh_degree):
     np.testing.assert_array_equal(bkt["keys_sorted"], binned["keys_sorted"])
     np.testing.assert_array_equal(bkt["vals_sorted"], binned["vals_sorted"])
     np.testing.assert_array_equal(bkt["ranges"], binned["ranges"])
+    # same again with the stand-alone count kernel instead of the count fused into preprocess
+    from cuda_stages import CudaPipeline
+    pipe2 = CudaPipeline(scene, cam, bg, sh_degree, fused_count=False)
+    pipe2.preprocess()
+    bkt2 = pipe2.bucket()
+    np.testing.assert_array_equal(bkt2["vals_sorted"], binned["vals_sorted"])
+    np.testing.assert_array_equal(bkt2["ranges"], binned["ranges"])
 
 
 @pytest.mark.parametrize("per_tile", [3000, 20000])
