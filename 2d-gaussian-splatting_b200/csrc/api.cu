@@ -185,7 +185,11 @@ int surfel_render_forward(const surfel_settings_t* s, uint32_t R, const void* ge
     p.bg = s->bg;
     p.out_color = out_color; p.out_others = out_others;
     p.accum = (float*)((char*)image_ws + I.accum); p.n_contrib = (uint32_t*)((char*)image_ws + I.n_contrib);
-    return launch_render_fwd(p, (cudaStream_t)stream);
+    // SURFEL_RENDER_FWD=g8 selects the experimental mapping "four 8-lane groups per warp, one splat
+    // per group" (render_fwd_g8.cu): 1.5x fewer blend rounds but measured SLOWER on B200 (0.487 ms vs
+    // 0.452 ms at the headline workload; 4 distinct smem addresses per load, no warp-uniform skips).
+    static const bool use_g8 = [] { const char* e = getenv("SURFEL_RENDER_FWD"); return e && !strcmp(e, "g8"); }();
+    return use_g8 ? launch_render_fwd_g8(p, (cudaStream_t)stream) : launch_render_fwd(p, (cudaStream_t)stream);
 }
 
 int surfel_bin_bucket(const surfel_settings_t* s, int P, uint32_t R, const void* geom_ws,

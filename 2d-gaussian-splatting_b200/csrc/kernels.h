@@ -77,5 +77,6 @@ int launch_bucket_binning(int P, size_t R, int gx, int gy, int row0, int row1, c
 
 int launch_render_fwd(const RenderParams& p, cudaStream_t stream);
 int launch_render_bwd(const RenderParams& p, cudaStream_t stream);
+int launch_render_fwd_g8(const RenderParams& p, cudaStream_t stream);   // 4 groups of 8 lanes per warp
 
 }  // namespace surfel
