@@ -375,3 +375,51 @@ def test_full_resolution_properties(oracle, cuda_lib, name, P):
     ref = oracle.backward(scene, cam, bg, pre, binned, dict(accum=gi["accum"], n_contrib=gi["n_contrib"]), gc.numpy(), go.numpy())
     for k in ("dL_dmeans3D", "dL_dscales", "dL_drotations", "dL_dopacity", "dL_dshs", "dL_dmeans2D"):
         grad_check(k, g1[k], ref[k])
+
+
+@pytest.mark.parametrize("sh_degree,M", [(0, 16), (2, 16), (2, 9), (0, 1), (3, 25)])
+def test_sh_degrees_and_coefficient_counts(oracle, cuda_lib, sh_degree, M):
+    """Active SH degree below the stored one (training raises it every 1000 iterations,
+    /root/reference/scene/gaussian_model.py oneupSHdegree) and M != 16 (scalar staging path)."""
+    from cuda_stages import CudaPipeline
+    case = dict(P=1500, W=200, H=120, seed=31, rotated=True, depth_complexity=25)
+    scene, cam = world_scene(**case)
+    rng = np.random.default_rng(M)
+    scene["shs"] = rng.normal(0, 0.4, (case["P"], M, 3)).astype(np.float32)
+    bg = np.array([0.3, 0.3, 0.3], np.float32)
+    pre, binned, img = oracle.forward(scene, cam, bg, sh_degree)
+    pipe = CudaPipeline(scene, cam, bg, sh_degree)
+    gp = pipe.preprocess()
+    vis = pre["radii"] > 0
+    np.testing.assert_array_equal(gp["radii"], pre["radii"])
+    np.testing.assert_allclose(gp["rgb"][vis], pre["rgb"][vis], atol=1e-6, rtol=0)
+    np.testing.assert_array_equal(gp["clamped"][vis], pre["clamped"][vis])
+    pipe.bucket(); gi = pipe.render()
+    assert_close_budget("color", gi["color"], img["color"])
+    gc, go = S.make_cotangents(cam["W"], cam["H"], 9)
+    ref = oracle.backward(scene, cam, bg, pre, binned, dict(accum=gi["accum"], n_contrib=gi["n_contrib"]),
+                          gc.numpy(), go.numpy(), sh_degree)
+    got = pipe.backward(gc.numpy(), go.numpy())
+    grad_check("dL_dshs", got["dL_dshs"], ref["dL_dshs"])
+    grad_check("dL_dmeans3D", got["dL_dmeans3D"], ref["dL_dmeans3D"])
+    ncoef = 3 * (sh_degree + 1) ** 2
+    assert (got["dL_dshs"].reshape(case["P"], -1)[:, ncoef:] == 0).all()      # inactive coefficients get zero gradient
+
+
+def test_scale_modifier_and_odd_sizes(oracle, cuda_lib):
+    """scale_modifier != 1 (the viewer path, /root/reference/view.py:24) and P / W / H that are not
+    multiples of any block size."""
+    from cuda_stages import CudaPipeline
+    case = dict(P=1237, W=253, H=141, seed=41, rotated=True, depth_complexity=30)
+    scene, cam = world_scene(**case)
+    bg = np.array([1.0, 1.0, 1.0], np.float32)
+    pre, binned, img = oracle.forward(scene, cam, bg, 3, 1.7)
+    pipe = CudaPipeline(scene, cam, bg, 3, 1.7)
+    gp = pipe.preprocess()
+    np.testing.assert_array_equal(gp["radii"], pre["radii"])
+    np.testing.assert_array_equal(gp["offsets"], binned["offsets"])
+    bk = pipe.bucket()
+    np.testing.assert_array_equal(bk["vals_sorted"], binned["vals_sorted"])
+    gi = pipe.render()
+    assert_close_budget("color", gi["color"], img["color"])
+    assert_close_budget("allmap", gi["others"], img["others"])
