@@ -29,7 +29,7 @@ constexpr int kRowQuads = 13;   // 12 data quads + 1 pad: conflict-free 128-bit 
 // access is a fully coalesced 128-bit transaction (M == 16, degree 3, 16-byte aligned tensors);
 // otherwise each thread addresses its own rows directly (any M / degree).
 template <bool kStaged>
-__global__ void __launch_bounds__(128) preprocess_bwd_kernel(PreBwdParams p) {
+__global__ void __launch_bounds__(128, 6) preprocess_bwd_kernel(PreBwdParams p) {
     __shared__ float4 s_rows[kStaged ? 4 * 32 * kRowQuads : 1];
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

@@ -68,7 +68,7 @@ constexpr int kShRowQuads = 13;                 // 12 data quads + 1 pad: confli
 constexpr int kShRowFloatsScalar = 49;          // scalar path stride (odd: conflict-free LDS.32)
 
 template <bool kVec4>
-__global__ void __launch_bounds__(kPreBlock, 6) preprocess_fwd_kernel(PreFwdParams p) {
+__global__ void __launch_bounds__(kPreBlock, 8) preprocess_fwd_kernel(PreFwdParams p) {
     __shared__ float4 s_sh[(kPreBlock / 32) * 32 * kShRowQuads];
     __shared__ int s_rows[kPreBlock];            // per warp: compacted list of visible lanes
     __shared__ uint32_t s_warp_sum[kPreBlock / 32];
