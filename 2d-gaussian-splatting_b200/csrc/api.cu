@@ -273,6 +273,7 @@ int surfel_mark_visible(int P, const float* means3D, const float* viewmatrix,
 }
 
 size_t surfel_sort_temp_bytes(size_t n) { return radix_sort_temp_bytes(n); }
+int surfel_grad_scratch_floats(void) { return kGradFloats; }
 
 int surfel_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
                       size_t n, int end_bit, void* temp, int* result_in_b, void* stream) {

@@ -35,10 +35,17 @@ constexpr int kChDepth = 0, kChAlpha = 1, kChNormal = 2, kChMidDepth = 5, kChDis
 constexpr int kRecQuads = 6;
 constexpr int kRecBytes = kRecQuads * 16;
 
-// Per-splat gradient record accumulated by render backward (float atomics), 20 floats = 80 B:
-//   [0..8] dL_dtransMat, [9..10] dL_dmean2D.xy, [11] dL_dopacity, [12..14] dL_dnormal,
-//   [15..17] dL_dcolor, [18..19] pad
-constexpr int kGradFloats = 20;
+// Per-splat gradient record accumulated by render backward (float atomics), 24 floats = 96 B.
+// dL_dtransMat is NOT accumulated directly: with dp = dL/d(cross(k,l)) per (pixel,splat) and
+// (dx,dy) = pixel - AABB centre, the sums  A = sum dp,  Bx = sum dx*dp,  By = sum dy*dp,
+// Z = sum dL_dz*(s.x, s.y, 1)  determine it exactly (the px*py terms cancel):
+//   dTu = -(lc x A) - (Tw x By),  dTv = -(A x kc) - (Bx x Tw),
+//   dTw = -cx*dTu - cy*dTv + lc x Bx + By x kc + Z,   kc = cx*Tw - Tu, lc = cy*Tw - Tv
+// which preprocess backward evaluates once per splat instead of every lane doing two cross products.
+//   [0..2] A  [3..5] Bx  [6..8] By  [9..11] Z  [12..13] dL_dmean2D.xy  [14] dL_dopacity
+//   [15..17] dL_dnormal  [18..20] dL_dcolor  [21..23] pad
+constexpr int kGradFloats = 24;
+constexpr int kGradUsed = 21;
 
 struct GeomLayout {
     size_t rec, tiles_touched, offsets, clamped, scan_status, counters, total;

@@ -47,14 +47,34 @@ __global__ void __launch_bounds__(128, 6) preprocess_bwd_kernel(PreBwdParams p) 
 
     if (visible) {
         const float4* gr = reinterpret_cast<const float4*>(p.grad_rec + (size_t)idx * kGradFloats);
-        const float4 a = gr[0], b = gr[1], c = gr[2], d = gr[3], e = gr[4];
-        gT[0] = a.x; gT[1] = a.y; gT[2] = a.z; gT[3] = a.w; gT[4] = b.x; gT[5] = b.y; gT[6] = b.z; gT[7] = b.w;
-        gT[8] = c.x; gm2x = c.y; gm2y = c.z; gopa = c.w;
-        gn[0] = d.x; gn[1] = d.y; gn[2] = d.z; gc[0] = d.w; gc[1] = e.x; gc[2] = e.y;
+        const float4 a = gr[0], b = gr[1], c = gr[2], d = gr[3], e = gr[4], f5 = gr[5];
         const float4* r = p.rec + (size_t)idx * kRecQuads;
         const float4 q0 = r[0], q1 = r[1], q2 = r[2];
         tm[0] = q0.x; tm[1] = q0.y; tm[2] = q0.z; tm[3] = q0.w; tm[4] = q1.x; tm[5] = q1.y;
         tm[6] = q1.z; tm[7] = q1.w; tm[8] = q2.x;
+        gm2x = d.x; gm2y = d.y; gopa = d.z;
+        gn[0] = d.w; gn[1] = e.x; gn[2] = e.y; gc[0] = e.z; gc[1] = e.w; gc[2] = f5.x;
+        {
+            // dL_dT from the accumulated sums A, Bx, By, Z (record layout: common.cuh)
+            const float A[3] = {a.x, a.y, a.z}, Bx[3] = {a.w, b.x, b.y}, By[3] = {b.z, b.w, c.x}, Z[3] = {c.y, c.z, c.w};
+            const float cx = q2.y, cy = q2.z;
+            const float kc[3] = {cx * tm[6] - tm[0], cx * tm[7] - tm[1], cx * tm[8] - tm[2]};
+            const float lc[3] = {cy * tm[6] - tm[3], cy * tm[7] - tm[4], cy * tm[8] - tm[5]};
+            const float* Tw = tm + 6;
+#define CROSS(o, u, v) do { o[0] = u[1] * v[2] - u[2] * v[1]; o[1] = u[2] * v[0] - u[0] * v[2]; o[2] = u[0] * v[1] - u[1] * v[0]; } while (0)
+            float t1[3], t2[3], t3[3], t4[3];
+            CROSS(t1, lc, A); CROSS(t2, Tw, By);          // dTu = -(lc x A) - (Tw x By)
+            CROSS(t3, A, kc); CROSS(t4, Bx, Tw);          // dTv = -(A x kc) - (Bx x Tw)
+            float u1[3], u2[3];
+            CROSS(u1, lc, Bx); CROSS(u2, By, kc);
+#undef CROSS
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                gT[k] = -t1[k] - t2[k];
+                gT[3 + k] = -t3[k] - t4[k];
+                gT[6 + k] = -cx * gT[k] - cy * gT[3 + k] + u1[k] + u2[k] + Z[k];
+            }
+        }
 
         // 1. AABB-centre vjp
         if (gm2x != 0.0f || gm2y != 0.0f) {

@@ -10,9 +10,10 @@
 //  * same 96-byte records / 8x4 warp footprints / bbox ballot culling as the forward (exact);
 //  * the CTA starts at the largest last_contributor of its pixels, not at the end of the list;
 //  * per (warp, splat) the lanes that really contribute (on average ~9 of 32 at 1 M splats / 1080p,
-//    ncu profiles/r1) are compacted with a ballot: each writes its 18 partials as one 80-byte row
-//    into a per-warp shared-memory panel, then 18 lanes each add one COLUMN of the panel and issue
-//    ONE red.global.add.f32 into the splat's 80-byte gradient record.  Work scales with the number
+//    ncu profiles/r1) are compacted with a ballot: each writes its 21 partials as one row
+//    into a per-warp shared-memory panel, then 21 lanes each add one COLUMN of the panel and issue
+//    ONE red.global.add.f32 into the splat's 96-byte gradient record (layout: common.cuh; the
+//    homography gradient is carried as the sums A, Bx, By, Z and finished in preprocess backward).  Work scales with the number
 //    of contributing lanes (a 32-lane shuffle butterfly cost 108 instructions per splat regardless),
 //    and global atomics drop from 18 per (pixel,splat) to 18 per (warp,splat), contiguous.
 #include "render_common.cuh"
@@ -24,12 +25,11 @@ namespace surfel {
 #ifndef SURFEL_BWD_BLOCKS
 #define SURFEL_BWD_BLOCKS 4
 #endif
-constexpr int kBatchB = 256;
-constexpr int kPanelRow = kGradFloats;            // 20 floats = 80 B per contributing lane
+constexpr int kBatchB = 192;                      // 18 KB of records + 28 KB panel fit the 48 KB static limit
+constexpr int kPanelRow = 28;                     // 21 used floats, 7-quad stride (odd: conflict-free STS.128)
 
 __global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(RenderParams p) {
-    __shared__ float4 s_rec[kRecQuads * kBatchB];            // [quad][slot]
-    __shared__ uint32_t s_id[kBatchB];
+    __shared__ float4 s_rec[kRecQuads * kBatchB];            // [quad][slot]; quad 4 .w carries the splat id
     __shared__ __align__(16) float s_panel[8 * 32 * kPanelRow];
     __shared__ uint32_t s_max[8];
 
@@ -94,10 +94,13 @@ __global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(Rend
         __syncthreads();
         if (tid < n) {
             const uint32_t id = p.point_list[range.x + start + tid];
-            s_id[tid] = id;
             const float4* r = p.rec + (size_t)id * kRecQuads;
 #pragma unroll
-            for (int q = 0; q < kRecQuads; q++) s_rec[q * kBatchB + tid] = __ldg(r + q);
+            for (int q = 0; q < kRecQuads; q++) {
+                float4 v = __ldg(r + q);
+                if (q == 4) v.w = __uint_as_float(id);
+                s_rec[q * kBatchB + tid] = v;
+            }
         }
         __syncthreads();
         if ((int)warp_max <= start) continue;   // nothing of this batch reaches this warp's pixels
@@ -143,42 +146,40 @@ __global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(Rend
                     dL_dz += 2.0f * w * (m_d * final_A - final_D) * dL_dreg * dmd_dd;
                     const float dL_dG = q2.w * dL_dalpha;
                     dL_dz += w * dL_ddepth;
-                    float g0 = 0, g1 = 0, g2 = 0, g3 = 0, g4 = 0, g5 = 0, g6 = 0, g7 = 0, g8, g9 = 0, g10 = 0;
+                    float ax = 0, ay = 0, az = 0, zx = 0, zy = 0, m2x = 0, m2y = 0;
                     if (e.use3d) {
                         const float Twx = q1.z, Twy = q1.w;
                         const float nG = -G * dL_dG;
                         const float dsx = nG * e.sx + dL_dz * Twx;
                         const float dsy = nG * e.sy + dL_dz * Twy;
-                        const float dpx = dsx * e.inv_pz, dpy = dsy * e.inv_pz;
-                        const float dpz = -(dpx * e.sx + dpy * e.sy);
-                        const float dkx = e.ly * dpz - e.lz * dpy, dky = e.lz * dpx - e.lx * dpz, dkz = e.lx * dpy - e.ly * dpx;
-                        const float dlx = dpy * e.kz - dpz * e.ky, dly = dpz * e.kx - dpx * e.kz, dlz = dpx * e.ky - dpy * e.kx;
-                        g0 = -dkx; g1 = -dky; g2 = -dkz;
-                        g3 = -dlx; g4 = -dly; g5 = -dlz;
-                        g6 = pxf * dkx + pyf * dlx + dL_dz * e.sx;
-                        g7 = pxf * dky + pyf * dly + dL_dz * e.sy;
-                        g8 = pxf * dkz + pyf * dlz + dL_dz;
+                        ax = dsx * e.inv_pz; ay = dsy * e.inv_pz;
+                        az = -(ax * e.sx + ay * e.sy);
+                        zx = dL_dz * e.sx; zy = dL_dz * e.sy;
                     } else {
                         const float gg = -G * kFilterInvSquare * dL_dG;
-                        g9 = gg * e.dx; g10 = gg * e.dy;
-                        if (p.lowpass_quirk) { g6 = e.sx * dL_dz; g7 = e.sy * dL_dz; }
-                        g8 = dL_dz;
+                        m2x = gg * e.dx; m2y = gg * e.dy;
+                        if (p.lowpass_quirk) { zx = e.sx * dL_dz; zy = e.sy * dL_dz; }
                     }
-                    // one 80-byte row per contributing lane (rows are compacted: ballot prefix)
+                    const float ndx = -e.dx, ndy = -e.dy;      // pixel - AABB centre
+                    // one row per contributing lane (rows are compacted: ballot prefix)
                     const uint32_t row = panel_base + __popc(am & lt_mask) * (kPanelRow * 4);
-                    sts128(row, make_float4(g0, g1, g2, g3));
-                    sts128(row + 16, make_float4(g4, g5, g6, g7));
-                    sts128(row + 32, make_float4(g8, g9, g10, G * dL_dalpha));
-                    sts128(row + 48, make_float4(w * dN0, w * dN1, w * dN2, w * dpix0));
-                    sts64(row + 64, w * dpix1, w * dpix2);
+                    sts128(row, make_float4(ax, ay, az, ndx * ax));
+                    sts128(row + 16, make_float4(ndx * ay, ndx * az, ndy * ax, ndy * ay));
+                    sts128(row + 32, make_float4(ndy * az, zx, zy, dL_dz));
+                    sts128(row + 48, make_float4(m2x, m2y, G * dL_dalpha, w * dN0));
+                    sts128(row + 64, make_float4(w * dN1, w * dN2, w * dpix0, w * dpix1));
+                    sts32(row + 80, w * dpix2);
                 }
                 __syncwarp();
-                if (lane < 18) {
+                if (lane < kGradUsed) {
                     const int nact = __popc(am);
                     uint32_t a = panel_base + lane * 4;
                     float acc = 0.0f;
                     for (int r = 0; r < nact; r++, a += kPanelRow * 4) acc += lds32(a);
-                    if (acc != 0.0f) atomicAdd(p.grad_rec + (size_t)s_id[k] * kGradFloats + lane, acc);
+                    if (acc != 0.0f) {
+                        const uint32_t id = __float_as_uint(lds32(ra + 4 * kBatchB * 16 + 12));
+                        atomicAdd(p.grad_rec + (size_t)id * kGradFloats + lane, acc);
+                    }
                 }
                 __syncwarp();
             }

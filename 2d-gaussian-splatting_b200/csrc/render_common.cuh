@@ -74,6 +74,9 @@ __device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
 __device__ __forceinline__ void sts64(uint32_t addr, float a, float b) {
     asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
 }
+__device__ __forceinline__ void sts32(uint32_t addr, float a) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(a) : "memory");
+}
 __device__ __forceinline__ float lds32(uint32_t addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));

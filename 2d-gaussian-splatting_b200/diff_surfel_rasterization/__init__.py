@@ -209,7 +209,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         d_sh = e(P, M, 3) if has_sh else None
         d_scales = e(P, 2) if has_scales else None
         d_rot = e(P, 4) if has_scales else None
-        scratch = e(max(P, 1), 20)
+        scratch = e(max(P, 1), lib.surfel_grad_scratch_floats())
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
             _cabi.check(lib.surfel_backward(

@@ -117,12 +117,13 @@ int surfel_render_forward(const surfel_settings_t* s, uint32_t R, const void* ge
                           const void* binning_ws, void* image_ws, float* out_color,
                           float* out_others, void* stream);
 
-/* Backward.  dL_dout_color (3,H,W), dL_dout_others (7,H,W).  grad_scratch: P*20 floats (zeroed
- * here).  Outputs are written for every splat (zeros where culled), so they may be uninitialised:
+/* Backward.  dL_dout_color (3,H,W), dL_dout_others (7,H,W).  grad_scratch: P *
+ * surfel_grad_scratch_floats() floats (zeroed here).  Outputs are written for every splat (zeros where culled), so they may be uninitialised:
  *   dL_dmeans2D (P,3) [densification proxy in .xy, SURVEY A.5], dL_dcolors (P,3),
  *   dL_dopacity (P,1), dL_dmeans3D (P,3), dL_dtransMat (P,9), dL_dsh (P,M,3),
  *   dL_dscales (P,2), dL_drotations (P,4).  Optional outputs may be NULL when the matching input
  *   is absent.  lowpass_depth_quirk: see DESIGN.md (default 0). */
+int surfel_grad_scratch_floats(void);
 int surfel_backward(const surfel_settings_t* s, int P, int M, uint32_t R, const float* means3D,
                     const float* scales, const float* rotations, const float* transMat_precomp,
                     const float* shs, int has_colors_precomp, const int32_t* radii,

@@ -125,7 +125,7 @@ class CudaPipeline:
         lib, P, M = self.lib, self.P, self.M
         gc, go = _t(dL_dcolor), _t(dL_dothers)
         e = lambda *s: torch.full(s, float("nan"), device="cuda")
-        scratch = e(max(P, 1), 20)
+        scratch = e(max(P, 1), lib.surfel_grad_scratch_floats())
         out = dict(dL_dmeans2D=e(P, 3), dL_dcolors=e(P, 3), dL_dopacity=e(P, 1), dL_dmeans3D=e(P, 3),
                    dL_dtransMat=e(P, 9), dL_dshs=e(P, max(M, 1), 3), dL_dscales=e(P, 2), dL_drotations=e(P, 4))
         _cabi.check(lib.surfel_backward(
