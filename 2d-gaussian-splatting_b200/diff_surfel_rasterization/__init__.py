@@ -72,17 +72,30 @@ def _ptr(t):
     return None if t is None or t.numel() == 0 else t.data_ptr()
 
 
+_struct_cache = {}          # id(settings) -> (settings, struct, tensors): tiny LRU, keeps the objects alive
+
+
 def _settings_struct(rs: GaussianRasterizationSettings, keep):
+    """ctypes view of the settings; cached per settings object (the same NamedTuple is used by the
+    forward and the backward of a call, and by every call of a long-lived GaussianRasterizer)."""
+    ent = _struct_cache.get(id(rs))
+    if ent is not None and ent[0] is rs:
+        keep.extend(ent[2])
+        return ent[1]
     bg = _dev_f32(rs.bg, "bg")
     vm = _dev_f32(rs.viewmatrix, "viewmatrix")
     pm = _dev_f32(rs.projmatrix, "projmatrix")
     cp = _dev_f32(rs.campos, "campos")
     keep.extend([bg, vm, pm, cp])
     rows = rs.tile_rows if len(rs) > 12 and rs.tile_rows is not None else (0, 0)
-    return _cabi.SurfelSettings(
+    cs = _cabi.SurfelSettings(
         int(rs.image_height), int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy),
         float(rs.scale_modifier), int(rs.sh_degree), int(bool(rs.prefiltered)), int(bool(rs.debug)),
         int(rows[0]), int(rows[1]), bg.data_ptr(), vm.data_ptr(), pm.data_ptr(), cp.data_ptr())
+    if len(_struct_cache) >= 16:
+        _struct_cache.pop(next(iter(_struct_cache)))
+    _struct_cache[id(rs)] = (rs, cs, [bg, vm, pm, cp])
+    return cs
 
 
 _pinned_counter = {}

@@ -243,7 +243,7 @@ def run_ours(args, rank, local_rank, world):
 
     # ---- resident-input throughput ("value") ----
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("SURFEL_BENCH_NOCLOCKS"):
         sampler.start()
     for _ in range(args.warmup):
         color, radii, allmap = step(leaf, means2D, gc, go)

@@ -15,7 +15,9 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 SHORT = {"render_fwd_kernel": "render_fwd", "render_bwd_kernel": "render_bwd", "preprocess_fwd_kernel": "preprocess_fwd",
          "preprocess_bwd_kernel": "preprocess_bwd", "radix_onesweep_kernel": "sort_onesweep_pass",
          "radix_histogram_kernel": "sort_histogram", "duplicate_with_keys_kernel": "duplicate_with_keys",
-         "identify_tile_ranges_kernel": "identify_tile_ranges", "radix_scan_hist_kernel": "sort_scan_hist"}
+         "identify_tile_ranges_kernel": "identify_tile_ranges", "radix_scan_hist_kernel": "sort_scan_hist",
+         "tile_count_kernel": "tile_count", "tile_scan_kernel": "tile_scan", "tile_scatter_kernel": "tile_scatter",
+         "tile_sort_small_kernel": "tile_sort", "tile_sort_large_kernel": "tile_sort_large"}
 
 
 def short(name):
