@@ -95,7 +95,7 @@ def test_preprocess_and_binning_bitexact(oracle, cuda_lib, case, sh_degree):
     np.testing.assert_array_equal(bkt2["ranges"], binned["ranges"])
 
 
-@pytest.mark.parametrize("per_tile", [3000, 20000])
+@pytest.mark.parametrize("per_tile", [700, 1500, 3000, 20000])
 def test_bucket_sort_crowded_tiles(oracle, cuda_lib, per_tile):
     """Thousands of splats piled onto a few tiles: exercises the large-tile (shared memory, 1024
     threads) and the global-memory fallback of the per-tile sort, plus equal-depth ties."""
