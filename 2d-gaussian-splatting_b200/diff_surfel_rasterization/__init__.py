@@ -175,6 +175,20 @@ class _RasterizeGaussians(torch.autograd.Function):
                     _cabi.check(lib.surfel_forward_render(
                         ctypes.byref(cs), P, cap, radii.data_ptr(), geom.data_ptr(), binning.data_ptr(),
                         img.data_ptr(), 1, color.data_ptr(), allmap.data_ptr(), stream))
+                # Everything the backward will need is allocated NOW, while the device is busy and before
+                # the host blocks: after the wait, the host's critical path to the backward launch (which
+                # must land before the queued forward kernels drain) is as short as possible.
+                if any(ctx.needs_input_grad[:8]):
+                    def e(*shape):
+                        return torch.empty(shape, dtype=torch.float32, device=dev)
+                    ctx.bwd_bufs = dict(
+                        d_means2D=e(P, 3), d_opacity=e(P, 1), d_means3D=e(P, 3),
+                        d_colors=e(P, 3) if colors_precomp is not None else None,
+                        d_cov=e(P, 9) if cov3Ds_precomp is not None else None,
+                        d_sh=e(P, M, 3) if sh is not None else None,
+                        d_scales=e(P, 2) if scales is not None else None,
+                        d_rot=e(P, 4) if scales is not None else None,
+                        scratch=e(max(P, 1), lib.surfel_grad_scratch_floats()))
                 ev.synchronize()
                 R = int(host_R.item()) & 0xFFFFFFFF
                 if R > cap or not cap:
@@ -216,13 +230,16 @@ class _RasterizeGaussians(torch.autograd.Function):
 
         def e(*shape):
             return torch.empty(shape, dtype=torch.float32, device=dev)
-        d_means2D, d_opacity, d_means3D = e(P, 3), e(P, 1), e(P, 3)
-        d_colors = e(P, 3) if has_colors else None
-        d_cov = e(P, 9) if has_cov else None
-        d_sh = e(P, M, 3) if has_sh else None
-        d_scales = e(P, 2) if has_scales else None
-        d_rot = e(P, 4) if has_scales else None
-        scratch = e(max(P, 1), lib.surfel_grad_scratch_floats())
+        b = getattr(ctx, "bwd_bufs", None)
+        if b is None:      # P == 0, or backward called twice (retain_graph): allocate here
+            b = dict(d_means2D=e(P, 3), d_opacity=e(P, 1), d_means3D=e(P, 3),
+                     d_colors=e(P, 3) if has_colors else None, d_cov=e(P, 9) if has_cov else None,
+                     d_sh=e(P, M, 3) if has_sh else None, d_scales=e(P, 2) if has_scales else None,
+                     d_rot=e(P, 4) if has_scales else None,
+                     scratch=e(max(P, 1), lib.surfel_grad_scratch_floats()))
+        ctx.bwd_bufs = None
+        d_means2D, d_opacity, d_means3D = b["d_means2D"], b["d_opacity"], b["d_means3D"]
+        d_colors, d_cov, d_sh, d_scales, d_rot, scratch = b["d_colors"], b["d_cov"], b["d_sh"], b["d_scales"], b["d_rot"], b["scratch"]
         stream = torch.cuda.current_stream(dev).cuda_stream
         with torch.cuda.device(dev):
             _cabi.check(lib.surfel_backward(

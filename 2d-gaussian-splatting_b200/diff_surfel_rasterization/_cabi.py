@@ -62,6 +62,17 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
+    if not os.path.exists(LIB_PATH) and not os.environ.get("SURFEL_LIB"):
+        # not built yet (fresh checkout): compile it in-tree with nvcc.  This is a BUILD step, not a
+        # fallback: if it fails there is no other implementation to fall back to.
+        try:
+            import importlib.util
+            spec = importlib.util.spec_from_file_location("surfel_b200_build", os.path.join(os.path.dirname(_HERE), "build.py"))
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            mod.build()
+        except Exception as ex:   # noqa: BLE001
+            raise ImportError(f"could not build {LIB_PATH} with nvcc: {ex}") from ex
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} not found: build the sm_100a CUDA library first "
