@@ -27,6 +27,7 @@ SOURCES = {
     "render_fwd.cu": [],
     "render_fwd_g8.cu": [],
     "render_bwd.cu": [],
+    "render_bwd_tma.cu": [],
 }
 
 

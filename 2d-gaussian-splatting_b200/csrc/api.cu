@@ -23,6 +23,11 @@ void surfel_set_error(const char* fmt, ...) {
 
 namespace {
 
+bool use_slab() {
+    static const bool v = [] { const char* e = getenv("SURFEL_RENDER_BWD"); return e && !strcmp(e, "tma"); }();
+    return v;
+}
+
 struct Frame { int W, H, gx, gy, row0, row1, tiles; };
 
 bool frame_of(const surfel_settings_t* s, Frame& f) {
@@ -56,11 +61,14 @@ BinningLayout binning_layout(size_t R, int tiles) {
     L.vals_b = o;    o = align_up(o + r * 4, 256);
     L.ranges = o;    o = align_up(o + (size_t)tiles * 8, 256);
     L.sort_temp = o; o = align_up(o + std::max(radix_sort_temp_bytes(r), bucket_temp_bytes(tiles)), 256);
+    // optional: per-tile SORTED slab of splat records (R x 96 B) written by the forward's staging and
+    // streamed back by the TMA backward with one bulk copy per stage (SURFEL_RENDER_BWD=tma only)
+    L.slab = o; if (use_slab()) o = align_up(o + r * kRecBytes, 256);
     L.total = o;
     return L;
 }
 
-struct BinView { uint64_t *k_unsorted, *k_sorted; uint32_t *v_unsorted, *v_sorted; uint64_t *k_a, *k_b; uint32_t *v_a, *v_b; uint2* ranges; void* temp; };
+struct BinView { uint64_t *k_unsorted, *k_sorted; uint32_t *v_unsorted, *v_sorted; uint64_t *k_a, *k_b; uint32_t *v_a, *v_b; uint2* ranges; void* temp; float4* slab; };
 
 BinView bin_view(void* ws, size_t R, const Frame& f) {
     BinningLayout L = binning_layout(R, f.tiles);
@@ -73,6 +81,7 @@ BinView bin_view(void* ws, size_t R, const Frame& f) {
     v.k_sorted = in_b ? v.k_b : v.k_a; v.v_sorted = in_b ? v.v_b : v.v_a;
     v.ranges = (uint2*)(c + L.ranges);
     v.temp = c + L.sort_temp;
+    v.slab = use_slab() ? (float4*)(c + L.slab) : nullptr;
     return v;
 }
 
@@ -185,6 +194,7 @@ int surfel_render_forward(const surfel_settings_t* s, uint32_t R, const void* ge
     p.bg = s->bg;
     p.out_color = out_color; p.out_others = out_others;
     p.accum = (float*)((char*)image_ws + I.accum); p.n_contrib = (uint32_t*)((char*)image_ws + I.n_contrib);
+    p.slab = v.slab;
     // SURFEL_RENDER_FWD=g8 selects the experimental mapping "four 8-lane groups per warp, one splat
     // per group" (render_fwd_g8.cu): 1.5x fewer blend rounds but measured SLOWER on B200 (0.487 ms vs
     // 0.452 ms at the headline workload; 4 distinct smem addresses per load, no warp-uniform skips).
@@ -249,8 +259,10 @@ int surfel_backward(const surfel_settings_t* s, int P, int M, uint32_t R, const 
         p.ranges = v.ranges; p.point_list = v.v_sorted; p.rec = (const float4*)(g + L.rec); p.bg = s->bg;
         p.accum = (float*)((char*)image_ws + I.accum); p.n_contrib = (uint32_t*)((char*)image_ws + I.n_contrib);
         p.dL_dpix = dL_dout_color; p.dL_dothers = dL_dout_others; p.grad_rec = grad_scratch;
+        p.slab = v.slab;
         p.lowpass_quirk = lowpass_depth_quirk;
-        if (launch_render_bwd(p, st)) return 1;
+        static const bool use_tma = [] { const char* e = getenv("SURFEL_RENDER_BWD"); return e && !strcmp(e, "tma"); }();
+        if (use_tma ? launch_render_bwd_tma(p, st) : launch_render_bwd(p, st)) return 1;
     }
     PreBwdParams q;
     memset(&q, 0, sizeof(q));

@@ -43,6 +43,7 @@ struct RenderParams {
     float* out_color; float* out_others; float* accum; uint32_t* n_contrib;
     // backward
     const float* dL_dpix; const float* dL_dothers; float* grad_rec; int lowpass_quirk;
+    float4* slab;   // optional (R x 6 quads): records in sorted tile-list order (forward writes, TMA backward reads)
 };
 
 int launch_preprocess_fwd(const PreFwdParams& p, cudaStream_t stream);
@@ -77,6 +78,7 @@ int launch_bucket_binning(int P, size_t R, int gx, int gy, int row0, int row1, c
 
 int launch_render_fwd(const RenderParams& p, cudaStream_t stream);
 int launch_render_bwd(const RenderParams& p, cudaStream_t stream);
+int launch_render_bwd_tma(const RenderParams& p, cudaStream_t stream);  // TMA bulk copy + mbarrier pipeline
 int launch_render_fwd_g8(const RenderParams& p, cudaStream_t stream);   // 4 groups of 8 lanes per warp
 
 }  // namespace surfel

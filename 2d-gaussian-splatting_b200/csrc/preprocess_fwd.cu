@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(kPreBlock, 8) preprocess_fwd_kernel(PreFwdPara
             r[1] = make_float4(tm[4], tm[5], tm[6], tm[7]);
             r[2] = make_float4(tm[8], cx, cy, opa);
             r[3] = make_float4(nrm[0], nrm[1], nrm[2], pvz);
-            r[4] = make_float4(rgb[0], rgb[1], rgb[2], 0.0f);
+            r[4] = make_float4(rgb[0], rgb[1], rgb[2], __uint_as_float((uint32_t)idx));   // .w: splat index (bits)
             r[5] = make_float4(bx0, by0, bx1, by1);
         }
     }

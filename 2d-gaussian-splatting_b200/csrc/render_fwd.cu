@@ -55,7 +55,11 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderParams p) {
             const uint32_t id = p.point_list[range.x + base + tid];
             const float4* r = p.rec + (size_t)id * kRecQuads;
 #pragma unroll
-            for (int q = 0; q < kRecQuads; q++) s_rec[q * kBatch + tid] = __ldg(r + q);
+            for (int q = 0; q < kRecQuads; q++) {
+                const float4 v = __ldg(r + q);
+                s_rec[q * kBatch + tid] = v;
+                if (p.slab) p.slab[(size_t)(range.x + base + tid) * kRecQuads + q] = v;
+            }
         }
         __syncthreads();
 
