@@ -23,10 +23,17 @@ void surfel_set_error(const char* fmt, ...) {
 
 namespace {
 
-bool use_slab() {
-    static const bool v = [] { const char* e = getenv("SURFEL_RENDER_BWD"); return e && !strcmp(e, "tma"); }();
+// Kernel variants (same architecture, alternative implementations kept for A/B measurement).
+// Defaults come from the environment once; surfel_set_variant() changes them at run time (tests).
+struct Variants { int sort_radix, fwd_g8, bwd_tma; };
+Variants& variants() {
+    static Variants v = [] {
+        auto is = [](const char* name, const char* val) { const char* e = getenv(name); return e && !strcmp(e, val) ? 1 : 0; };
+        return Variants{is("SURFEL_SORT", "radix"), is("SURFEL_RENDER_FWD", "g8"), is("SURFEL_RENDER_BWD", "tma")};
+    }();
     return v;
 }
+bool use_slab() { return variants().bwd_tma != 0; }
 
 struct Frame { int W, H, gx, gy, row0, row1, tiles; };
 
@@ -90,7 +97,27 @@ BinView bin_view(void* ws, size_t R, const Frame& f) {
 extern "C" {
 
 int surfel_abi_version(void) { return SURFEL_ABI_VERSION; }
+
+int surfel_set_variant(const char* name, const char* value) {
+    if (!name || !value) { surfel_set_error("surfel_set_variant: NULL argument"); return 1; }
+    Variants& v = variants();
+    if (!strcmp(name, "sort")) {
+        if (!strcmp(value, "bucket")) v.sort_radix = 0; else if (!strcmp(value, "radix")) v.sort_radix = 1; else goto bad;
+    } else if (!strcmp(name, "render_fwd")) {
+        if (!strcmp(value, "warp")) v.fwd_g8 = 0; else if (!strcmp(value, "g8")) v.fwd_g8 = 1; else goto bad;
+    } else if (!strcmp(name, "render_bwd")) {
+        if (!strcmp(value, "classic")) v.bwd_tma = 0; else if (!strcmp(value, "tma")) v.bwd_tma = 1; else goto bad;
+    } else goto bad;
+    return 0;
+bad:
+    surfel_set_error("surfel_set_variant: unknown variant %s=%s", name, value);
+    return 1;
+}
 const char* surfel_last_error(void) { return g_err; }
+
+// 1 iff surfel_forward_render accepts an UPPER BOUND of the instance count as R (speculative launch):
+// true for the tile-bucketed binning, false for the device-wide radix sort (it sorts exactly R pairs).
+int surfel_accepts_capacity(void) { return variants().sort_radix ? 0 : 1; }
 
 size_t surfel_geom_bytes(int P) { return geom_layout(P).total; }
 size_t surfel_image_bytes(int W, int H) { return image_layout(W, H).total; }
@@ -198,7 +225,7 @@ int surfel_render_forward(const surfel_settings_t* s, uint32_t R, const void* ge
     // SURFEL_RENDER_FWD=g8 selects the experimental mapping "four 8-lane groups per warp, one splat
     // per group" (render_fwd_g8.cu): 1.5x fewer blend rounds but measured SLOWER on B200 (0.487 ms vs
     // 0.452 ms at the headline workload; 4 distinct smem addresses per load, no warp-uniform skips).
-    static const bool use_g8 = [] { const char* e = getenv("SURFEL_RENDER_FWD"); return e && !strcmp(e, "g8"); }();
+    const bool use_g8 = variants().fwd_g8 != 0;
     return use_g8 ? launch_render_fwd_g8(p, (cudaStream_t)stream) : launch_render_fwd(p, (cudaStream_t)stream);
 }
 
@@ -224,7 +251,7 @@ int surfel_forward_render(const surfel_settings_t* s, int P, uint32_t R, const i
                           const void* geom_ws, void* binning_ws, void* image_ws, int tile_counts_ready,
                           float* out_color, float* out_others, void* stream) {
     // SURFEL_SORT=radix selects the device-wide onesweep radix sort instead of the tile-bucketed path
-    static const bool use_radix = [] { const char* e = getenv("SURFEL_SORT"); return e && !strcmp(e, "radix"); }();
+    const bool use_radix = variants().sort_radix != 0;
     if (!use_radix) {
         if (surfel_bin_bucket(s, P, R, geom_ws, radii, binning_ws, tile_counts_ready ? image_ws : nullptr, 0, stream)) return 1;
         return surfel_render_forward(s, R, geom_ws, binning_ws, image_ws, out_color, out_others, stream);
@@ -261,7 +288,7 @@ int surfel_backward(const surfel_settings_t* s, int P, int M, uint32_t R, const 
         p.dL_dpix = dL_dout_color; p.dL_dothers = dL_dout_others; p.grad_rec = grad_scratch;
         p.slab = v.slab;
         p.lowpass_quirk = lowpass_depth_quirk;
-        static const bool use_tma = [] { const char* e = getenv("SURFEL_RENDER_BWD"); return e && !strcmp(e, "tma"); }();
+        const bool use_tma = variants().bwd_tma != 0 && v.slab != nullptr;
         if (use_tma ? launch_render_bwd_tma(p, st) : launch_render_bwd(p, st)) return 1;
     }
     PreBwdParams q;

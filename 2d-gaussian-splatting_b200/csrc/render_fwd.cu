@@ -55,10 +55,11 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderParams p) {
             const uint32_t id = p.point_list[range.x + base + tid];
             const float4* r = p.rec + (size_t)id * kRecQuads;
 #pragma unroll
-            for (int q = 0; q < kRecQuads; q++) {
-                const float4 v = __ldg(r + q);
-                s_rec[q * kBatch + tid] = v;
-                if (p.slab) p.slab[(size_t)(range.x + base + tid) * kRecQuads + q] = v;
+            for (int q = 0; q < kRecQuads; q++) s_rec[q * kBatch + tid] = __ldg(r + q);
+            if (p.slab) {      // TMA-backward variant only: also lay the records out in sorted order
+                float4* dst = p.slab + (size_t)(range.x + base + tid) * kRecQuads;
+#pragma unroll
+                for (int q = 0; q < kRecQuads; q++) dst[q] = s_rec[q * kBatch + tid];
             }
         }
         __syncthreads();

@@ -110,7 +110,7 @@ def last_num_rendered():
 
 _capacity = {}
 # SURFEL_SPECULATIVE=0 restores upstream's launch order (block on R, then launch binning + render)
-_SPECULATIVE = bool(int(os.environ.get("SURFEL_SPECULATIVE", "1"))) and os.environ.get("SURFEL_SORT", "") != "radix"
+_SPECULATIVE = bool(int(os.environ.get("SURFEL_SPECULATIVE", "1")))
 
 
 def _pinned_u32(device):
@@ -169,7 +169,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                 # then wait for R: the device keeps working while the host waits, and the wait ends as
                 # soon as preprocess is done.  A too-small guess costs one re-launch.
                 key = (dev.index, P, W, H, cs.tile_row_begin, cs.tile_row_end)
-                cap = _capacity.get(key, 0) if _SPECULATIVE else 0
+                spec = _SPECULATIVE and lib.surfel_accepts_capacity()
+                cap = _capacity.get(key, 0) if spec else 0
                 if cap:
                     binning = torch.empty((lib.surfel_binning_bytes(cap, W, H),), dtype=torch.uint8, device=dev)
                     _cabi.check(lib.surfel_forward_render(
@@ -192,8 +193,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                 ev.synchronize()
                 R = int(host_R.item()) & 0xFFFFFFFF
                 if R > cap or not cap:
-                    cap = R if not _SPECULATIVE else int(R * 1.25) + 4096
-                    _capacity[key] = cap
+                    cap = R if not spec else int(R * 1.25) + 4096
+                    if spec:
+                        _capacity[key] = cap
                     binning = None
             if P == 0 or binning is None:
                 binning = torch.empty((lib.surfel_binning_bytes(cap, W, H),), dtype=torch.uint8, device=dev)

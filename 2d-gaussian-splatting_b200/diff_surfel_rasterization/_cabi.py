@@ -29,6 +29,8 @@ class SurfelSettings(ctypes.Structure):
 SIGNATURES = {
     "surfel_abi_version": (c_int, []),
     "surfel_last_error": (ctypes.c_char_p, []),
+    "surfel_accepts_capacity": (c_int, []),
+    "surfel_set_variant": (c_int, [ctypes.c_char_p, ctypes.c_char_p]),
     "surfel_geom_bytes": (c_size_t, [c_int]),
     "surfel_image_bytes": (c_size_t, [c_int, c_int]),
     "surfel_binning_bytes": (c_size_t, [c_size_t, c_int, c_int]),

@@ -68,6 +68,16 @@ typedef struct surfel_settings {
 int surfel_abi_version(void);
 const char* surfel_last_error(void);
 
+/* Selects between alternative implementations of the same stage (all sm_100a; kept for A/B
+ * measurement): "sort" = "bucket" (default) | "radix"; "render_fwd" = "warp" (default) |
+ * "g8"; "render_bwd" = "classic" (default) | "tma".  Environment defaults: SURFEL_SORT,
+ * SURFEL_RENDER_FWD, SURFEL_RENDER_BWD.  Affects workspace sizes: set it before sizing buffers and do
+ * not change it between a forward and its backward. */
+int surfel_set_variant(const char* name, const char* value);
+/* 1 iff R passed to surfel_forward_render / surfel_backward may be an upper bound ("capacity") of the
+ * true instance count, which lets the caller launch stage 2 before it has read R back. */
+int surfel_accepts_capacity(void);
+
 /* Workspace sizes (bytes).  R = number of (splat, tile) instances ("num_rendered"). */
 size_t surfel_geom_bytes(int P);
 size_t surfel_image_bytes(int W, int H);

@@ -423,3 +423,40 @@ def test_scale_modifier_and_odd_sizes(oracle, cuda_lib):
     gi = pipe.render()
     assert_close_budget("color", gi["color"], img["color"])
     assert_close_budget("allmap", gi["others"], img["others"])
+
+
+@pytest.mark.parametrize("variant", [("sort", "radix", "bucket"), ("render_fwd", "g8", "warp"), ("render_bwd", "tma", "classic")])
+def test_alternative_kernel_variants(oracle, cuda_lib, variant):
+    """The selectable alternatives (device-wide radix sort, 8-lane-group forward, TMA/mbarrier backward)
+    must meet the same parity bar as the defaults, end to end through the public API."""
+    from diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    name, alt, default = variant
+    case = CASES[0]
+    scene, cam = world_scene(**case)
+    bg = np.array([0.1, 0.2, 0.3], np.float32)
+    pre, binned, img = oracle.forward(scene, cam, bg)
+    gc, go = S.make_cotangents(cam["W"], cam["H"], 3)
+    ref = oracle.backward(scene, cam, bg, pre, binned, img, gc.numpy(), go.numpy())
+    dev = "cuda"
+    assert cuda_lib.surfel_set_variant(name.encode(), alt.encode()) == 0
+    try:
+        t = lambda a: torch.tensor(a, device=dev, requires_grad=True)
+        leaf = {k: t(scene[k]) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+        m2d = torch.zeros(case["P"], 3, device=dev, requires_grad=True)
+        rs = GaussianRasterizationSettings(
+            image_height=cam["H"], image_width=cam["W"], tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"],
+            bg=torch.tensor(bg, device=dev), scale_modifier=1.0, viewmatrix=torch.tensor(cam["viewmatrix"], device=dev),
+            projmatrix=torch.tensor(cam["projmatrix"], device=dev), sh_degree=3, campos=torch.tensor(cam["campos"], device=dev),
+            prefiltered=False, debug=False)
+        color, radii, allmap = GaussianRasterizer(rs)(means3D=leaf["means3D"], means2D=m2d, shs=leaf["shs"],
+                                                      opacities=leaf["opacities"], scales=leaf["scales"], rotations=leaf["rotations"])
+        (color * gc.cuda()).sum().add((allmap * go.cuda()).sum()).backward()
+        torch.cuda.synchronize()
+    finally:
+        assert cuda_lib.surfel_set_variant(name.encode(), default.encode()) == 0
+    np.testing.assert_array_equal(radii.cpu().numpy(), pre["radii"])
+    assert_close_budget("color", color.detach().cpu().numpy(), img["color"])
+    assert_close_budget("allmap", allmap.detach().cpu().numpy(), img["others"])
+    grad_check("means3D.grad", leaf["means3D"].grad.cpu().numpy(), ref["dL_dmeans3D"], budget=1e-2)
+    grad_check("shs.grad", leaf["shs"].grad.cpu().numpy(), ref["dL_dshs"], budget=1e-2)
+    grad_check("opacity.grad", leaf["opacities"].grad.cpu().numpy(), ref["dL_dopacity"], budget=1e-2)
