@@ -32,6 +32,7 @@ def main():
     here = os.path.dirname(os.path.abspath(__file__))
     out = [f"# ncu summary, round {tag} (headline workload: 1 M surfels, 1920x1080, fwd+bwd)\n"]
     traffic = {}
+    stats = {}
     for rep in reps:
         raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(raw.splitlines()))
@@ -44,6 +45,15 @@ def main():
             vals = [r[hdr.index(w)] if w in hdr else "" for w in WANT]
             out.append(f"| {name.split('(')[0][-40:]} | " + " | ".join(vals) + " |")
             s = short(name)
+            if s:
+                def val(w):
+                    return float(r[hdr.index(w)]) if w in hdr and r[hdr.index(w)] not in ("", "n/a") else None
+                stats[s] = {"issue_active_pct": val("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                            "warps_active_pct": val("sm__warps_active.avg.pct_of_peak_sustained_active"),
+                            "warp_instructions": val("smsp__inst_executed.sum"),
+                            "dram_throughput_pct": val("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                            "registers_per_thread": val("launch__registers_per_thread"),
+                            "source": os.path.basename(rep)}
             if s and "dram__bytes_read.sum" in hdr:
                 unit = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
                 rd = float(r[hdr.index("dram__bytes_read.sum")]) * unit[rows[1][hdr.index("dram__bytes_read.sum")]]
@@ -68,6 +78,10 @@ def main():
     old = json.load(open(tpath)) if os.path.exists(tpath) else {}
     old.update(traffic)
     json.dump(old, open(tpath, "w"), indent=1, sort_keys=True)
+    spath = os.path.join(here, "ncu_kernel_stats.json")
+    olds = json.load(open(spath)) if os.path.exists(spath) else {}
+    olds.update(stats)
+    json.dump(olds, open(spath, "w"), indent=1, sort_keys=True)
     print("\n".join(out[-12:]))
 
 
