@@ -28,6 +28,7 @@ SOURCES = {
     "render_fwd_g8.cu": [],
     "render_bwd.cu": [],
     "render_bwd_tma.cu": [],
+    "postprocess.cu": [],
 }
 
 

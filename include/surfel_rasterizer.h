@@ -153,6 +153,20 @@ size_t surfel_sort_temp_bytes(size_t n);
 int surfel_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b,
                       size_t n, int end_bit, void* temp, int* result_in_b, void* stream);
 
+/* OPT-IN fused post-process of the op's allmap: what the reference's render() does
+ * with ~10 PyTorch kernels per direction at /root/reference/gaussian_renderer/__init__.py:118-147 and
+ * /root/reference/utils/point_utils.py:9-37.  rot (9): n_world = n_view . rot (= world_view[:3,:3]^T);
+ * rays (12): 3x3 pixel->world ray matrix (row-major, dir = (x,y,1).M) followed by the camera centre.
+ * Outputs: rend_normal (3,H,W), surf_depth (1,H,W), surf_normal (3,H,W).  Backward: cotangents of the
+ * three outputs (any may be NULL), tmp6 = (6,H,W) scratch, g_allmap (7,H,W) fully written. */
+int surfel_post_forward(int W, int H, float depth_ratio, const float* allmap, const float* rot,
+                        const float* rays, float* rend_normal, float* surf_depth, float* surf_normal,
+                        void* stream);
+int surfel_post_backward(int W, int H, float depth_ratio, const float* allmap, const float* rot,
+                         const float* rays, const float* surf_depth, const float* g_rend_normal,
+                         const float* g_surf_depth, const float* g_surf_normal, float* tmp6,
+                         float* g_allmap, void* stream);
+
 /* Instrumentation used by bench.py: number of kernels this library has launched in this process,
  * and optional per-stage CUDA-event timing (events recorded on the launching stream around each
  * kernel while enabled; surfel_profile_read() waits for them and returns summed ms / launch counts
