@@ -29,6 +29,7 @@ SOURCES = {
     "render_bwd.cu": [],
     "render_bwd_tma.cu": [],
     "postprocess.cu": [],
+    "loss.cu": [],
 }
 
 

@@ -50,6 +50,8 @@ SIGNATURES = {
     "surfel_sort_temp_bytes": (c_size_t, [c_size_t]),
     "surfel_post_forward": (c_int, [c_int, c_int, c_float] + [c_void_p] * 6 + [c_void_p]),
     "surfel_post_backward": (c_int, [c_int, c_int, c_float] + [c_void_p] * 9 + [c_void_p]),
+    "surfel_l1_ssim_forward": (c_int, [c_int, c_int, c_int] + [c_void_p] * 6 + [c_void_p]),
+    "surfel_l1_ssim_backward": (c_int, [c_int, c_int, c_int] + [c_void_p] * 7 + [c_void_p]),
     "surfel_launch_count": (ctypes.c_ulonglong, []),
     "surfel_profile_enable": (None, [c_int]),
     "surfel_profile_num_stages": (c_int, []),

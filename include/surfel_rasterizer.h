@@ -167,6 +167,17 @@ int surfel_post_backward(int W, int H, float depth_ratio, const float* allmap, c
                          const float* g_surf_depth, const float* g_surf_normal, float* tmp6,
                          float* g_allmap, void* stream);
 
+/* OPT-IN fused photometric loss: (1-l)*L1 + l*(1-SSIM) of
+ * /root/reference/train.py:73-74 with /root/reference/utils/loss_utils.py:6-7, :43-73 (11x11 Gaussian
+ * window, sigma 1.5, zero padding, per channel).  forward: sums2[0] = sum |img-gt|, sums2[1] = sum of
+ * the SSIM map (doubles, device) and the three (C,H,W) derivative maps the backward consumes.
+ * backward: gscale2 (device, 2 floats) = dL/d(sums2); g_img (C,H,W) fully written. */
+int surfel_l1_ssim_forward(int C, int H, int W, const float* img, const float* gt, float* dmu1,
+                           float* ds11, float* ds12, double* sums2, void* stream);
+int surfel_l1_ssim_backward(int C, int H, int W, const float* img, const float* gt, const float* dmu1,
+                            const float* ds11, const float* ds12, const float* gscale2, float* g_img,
+                            void* stream);
+
 /* Instrumentation used by bench.py: number of kernels this library has launched in this process,
  * and optional per-stage CUDA-event timing (events recorded on the launching stream around each
  * kernel while enabled; surfel_profile_read() waits for them and returns summed ms / launch counts
