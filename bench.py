@@ -129,6 +129,32 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "note": note}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, BEFORE any pinned host memory is
+    allocated, so that the e2e leg's H2D/D2H copies do not cross the socket interconnect.  Best effort:
+    returns the node id or None."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return None
+        if bus.startswith("00000000:"):
+            bus = bus[4:]                                    # sysfs uses a 4-digit PCI domain
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def cpu_oracle_run(scene_np, cam_np, gc, go, P, max_seconds=25.0):
     """C-oracle (OpenMP, all host cores) fwd+bwd.  Full workload if it fits the time budget, else a
     bounded sample: a band of tile rows of the same frame (all P splats are still preprocessed)."""
@@ -205,6 +231,7 @@ def run_ours(args, rank, local_rank, world):
     from diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer, _cabi
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    numa_node = None if os.environ.get("SURFEL_BENCH_NO_NUMA") else bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     lib = _cabi.load()
@@ -356,6 +383,10 @@ def run_ours(args, rank, local_rank, world):
     # ---- CPU baseline on rank 0 (N == 1 only) ----
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            os.sched_setaffinity(0, range(os.cpu_count()))   # the CPU leg uses every host core again
+        except Exception:
+            pass
         sn, cn = S.to_numpy(scene), S.to_numpy(cam)
         v, dt, sample = cpu_oracle_run(sn, cn, gc_h.numpy(), go_h.numpy(), P, max_seconds=20.0)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
@@ -383,6 +414,7 @@ def run_ours(args, rank, local_rank, world):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {P} surfels, {W}x{H}, SH degree 3, fwd+bwd, one view per GPU",
                        "visible": V, "instances": R, "parallelism": f"view-parallel x{world} (no collective)",
+                       "host_numa_node": numa_node,
                        "l2_policy": "inputs larger than L2 (232 MB of splat parameters + 83 MB of outputs per step vs 126 MB L2)"},
             "e2e": e2e, "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
             "roofline": roofline, "clocks": clocks,
