@@ -21,7 +21,8 @@ namespace surfel {
 
 constexpr int kBatch = 256;
 
-__global__ void __launch_bounds__(256) render_fwd_kernel(RenderParams p) {
+template <bool kSlab>   // kSlab: also lay the staged records out in sorted order (TMA-backward variant only)
+__global__ void __launch_bounds__(256, 5) render_fwd_kernel(RenderParams p) {
     __shared__ float4 s_rec[kRecQuads * kBatch];     // [quad][slot]
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -56,7 +57,7 @@ __global__ void __launch_bounds__(256) render_fwd_kernel(RenderParams p) {
             const float4* r = p.rec + (size_t)id * kRecQuads;
 #pragma unroll
             for (int q = 0; q < kRecQuads; q++) s_rec[q * kBatch + tid] = __ldg(r + q);
-            if (p.slab) {      // TMA-backward variant only: also lay the records out in sorted order
+            if (kSlab) {
                 float4* dst = p.slab + (size_t)(range.x + base + tid) * kRecQuads;
 #pragma unroll
                 for (int q = 0; q < kRecQuads; q++) dst[q] = s_rec[q * kBatch + tid];
@@ -132,7 +133,8 @@ int launch_render_fwd(const RenderParams& p, cudaStream_t stream) {
     if (rows <= 0 || p.gx <= 0) return 0;
     dim3 grid(p.gx, rows);
     LaunchScope scope(kStRenderFwd, stream);
-    render_fwd_kernel<<<grid, 256, 0, stream>>>(p);
+    if (p.slab) render_fwd_kernel<true><<<grid, 256, 0, stream>>>(p);
+    else        render_fwd_kernel<false><<<grid, 256, 0, stream>>>(p);
     SURFEL_CUDA_OK(cudaGetLastError());
     return 0;
 }

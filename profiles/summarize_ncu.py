@@ -17,7 +17,8 @@ SHORT = {"render_fwd_kernel": "render_fwd", "render_bwd_kernel": "render_bwd", "
          "radix_histogram_kernel": "sort_histogram", "duplicate_with_keys_kernel": "duplicate_with_keys",
          "identify_tile_ranges_kernel": "identify_tile_ranges", "radix_scan_hist_kernel": "sort_scan_hist",
          "tile_count_kernel": "tile_count", "tile_scan_kernel": "tile_scan", "tile_scatter_kernel": "tile_scatter",
-         "tile_sort_small_kernel": "tile_sort", "tile_sort_large_kernel": "tile_sort_large"}
+         "tile_sort_warp_kernel": "tile_sort", "tile_sort_small_kernel": "tile_sort_mid",
+         "tile_sort_large_kernel": "tile_sort_large"}
 
 
 def short(name):
