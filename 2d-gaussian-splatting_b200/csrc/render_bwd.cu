@@ -25,7 +25,10 @@ namespace surfel {
 #ifndef SURFEL_BWD_BLOCKS
 #define SURFEL_BWD_BLOCKS 4
 #endif
-constexpr int kBatchB = 192;                      // 18 KB of records + 28 KB panel fit the 48 KB static limit
+#ifndef SURFEL_BWD_BATCH
+#define SURFEL_BWD_BATCH 192
+#endif
+constexpr int kBatchB = SURFEL_BWD_BATCH;   // 18 KB of records + 28 KB panel fit the 48 KB static limit
 constexpr int kPanelRow = 28;                     // 21 used floats, 7-quad stride (odd: conflict-free STS.128)
 
 __global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(RenderParams p) {

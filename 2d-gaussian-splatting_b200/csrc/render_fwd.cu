@@ -19,7 +19,10 @@
 
 namespace surfel {
 
-constexpr int kBatch = 256;
+#ifndef SURFEL_FWD_BATCH
+#define SURFEL_FWD_BATCH 256
+#endif
+constexpr int kBatch = SURFEL_FWD_BATCH;
 
 template <bool kSlab>   // kSlab: also lay the staged records out in sorted order (TMA-backward variant only)
 __global__ void __launch_bounds__(256, 5) render_fwd_kernel(RenderParams p) {
