@@ -116,15 +116,17 @@ __global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(Rend
                 hit = bb.x <= fx1 && bb.z >= fx0 && bb.y <= fy1 && bb.w >= fy0;
             }
             unsigned m = __ballot_sync(0xffffffffu, hit);
+            uint32_t gb = rec_base + (uint32_t)c * 16u;
+            asm volatile("" : "+r"(gb));      // keep it in a register (else re-derived from SR_CgaCtaId per hit)
+            const int own = (int)last_contributor - (start + c);      // bits below `own` are this pixel's
+            const int med = (int)median_index - (start + c);
             while (m) {
-                const int j = 31 - __clz(m);
-                m &= ~(1u << j);
-                const int k = c + j;
-                const uint32_t index = (uint32_t)(start + k);   // 0-based contributor
-                const uint32_t ra = rec_base + k * 16;
+                const uint32_t j = high_bit(m);                       // back to front
+                m &= low_mask(j);
+                const uint32_t ra = gb + j * 16u;
                 const float4 q0 = lds128(ra), q1 = lds128(ra + kBatchB * 16), q2 = lds128(ra + 2 * kBatchB * 16);
                 PairEval e;
-                const bool active = index < last_contributor && eval_pair(pxf, pyf, q0, q1, q2, e);
+                const bool active = (int)j < own && eval_pair(pxf, pyf, q0, q1, q2, e);
                 const unsigned am = __ballot_sync(0xffffffffu, active);
                 if (am == 0u) continue;
 
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(Rend
                     v = fmaf(q3.x, dN0, v); v = fmaf(q3.y, dN1, v); v = fmaf(q3.z, dN2, v);
                     const float dL_dalpha = T * v - (S - bgT) * inv1ma;
                     S = fmaf(w, v, S);
-                    float dL_dz = (index == median_index) ? dL_dmedian : 0.0f;
+                    float dL_dz = ((int)j == med) ? dL_dmedian : 0.0f;
                     dL_dz += 2.0f * w * (m_d * final_A - final_D) * dL_dreg * dmd_dd;
                     const float dL_dG = q2.w * dL_dalpha;
                     dL_dz += w * dL_ddepth;

@@ -58,6 +58,19 @@ __device__ __forceinline__ bool eval_pair(float pxf, float pyf, const float4& q0
     return true;
 }
 
+// Position of the highest set bit (FLO) and the mask of the bits below a position (BMSK): the hit
+// loops of the render kernels peel ballot bits with exactly these two instructions.
+__device__ __forceinline__ uint32_t high_bit(uint32_t m) {
+    uint32_t r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(m));
+    return r;
+}
+__device__ __forceinline__ uint32_t low_mask(uint32_t width) {
+    uint32_t r;
+    asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(r) : "r"(width));
+    return r;
+}
+
 // Explicit shared-window addressing: one cvta per kernel instead of a generic->shared conversion
 // (S2UR CgaCtaId + ULEA) re-materialised in every inner-loop iteration.
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

@@ -46,9 +46,9 @@ __global__ void __launch_bounds__(256, 5) render_fwd_kernel(RenderParams p) {
 
     float T = 1.0f, C0 = 0, C1 = 0, C2 = 0, N0 = 0, N1 = 0, N2 = 0, D = 0, M1 = 0, M2 = 0, dist = 0;
     float median_depth = 0;
-    uint32_t last_contributor = 0, median_contributor = 0xFFFFFFFFu;
-    bool done = !inside;
-    bool warp_done = __all_sync(0xffffffffu, done);
+    uint32_t last_contributor = inside ? 0u : 0x80000000u;   // top bit: this pixel is finished
+    uint32_t median_contributor = 0xFFFFFFFFu;
+    bool warp_done = __all_sync(0xffffffffu, !inside);
 
     for (int base = 0; base < total; base += kBatch) {
         // CTA-wide early out (also orders the previous batch's smem reads before this refill)
@@ -76,39 +76,40 @@ __global__ void __launch_bounds__(256, 5) render_fwd_kernel(RenderParams p) {
                     const float4 bb = lds128(rec_base + (5 * kBatch + slot) * 16);
                     hit = bb.x <= fx1 && bb.z >= fx0 && bb.y <= fy1 && bb.w >= fy0;
                 }
-                unsigned m = __ballot_sync(0xffffffffu, hit);
-                while (m) {
-                    const int j = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int k = c + j;
-                    if (!done) {
-                        const uint32_t ra = rec_base + k * 16;
+                // bit 31 = slot c: taking the highest set bit first walks the hits front to back
+                unsigned m = __brev(__ballot_sync(0xffffffffu, hit));
+                // The hit loop holds no warp-synchronous operation, so finished pixels simply skip it
+                // and a pixel that saturates leaves it early.  "Finished" is the top bit of
+                // last_contributor (lists are far shorter than 2^31).
+                if ((int)last_contributor >= 0) {
+                    const uint32_t g31 = rec_base + (uint32_t)(c + 31) * 16u;
+                    const uint32_t k32 = (uint32_t)(base + c + 32);
+                    while (m) {
+                        const uint32_t hb = high_bit(m);               // slot c + 31 - hb
+                        m &= low_mask(hb);
+                        const uint32_t ra = g31 - hb * 16u;
                         const float4 q0 = lds128(ra), q1 = lds128(ra + kBatch * 16), q2 = lds128(ra + 2 * kBatch * 16);
                         PairEval e;
-                        if (eval_pair(pxf, pyf, q0, q1, q2, e)) {
-                            const float test_T = T * (1.0f - e.alpha);
-                            if (test_T < kTMin) {
-                                done = true;
-                            } else {
-                                const uint32_t contributor = (uint32_t)(base + k + 1);
-                                const float4 q3 = lds128(ra + 3 * kBatch * 16), q4 = lds128(ra + 4 * kBatch * 16);
-                                const float w = e.alpha * T;
-                                const float A = 1.0f - T;
-                                const float mm = kMScale * (1.0f - kNear * fast_rcp(e.depth));
-                                dist += (mm * mm * A + M2 - 2.0f * mm * M1) * w;
-                                D += e.depth * w;
-                                M1 += mm * w;
-                                M2 += mm * mm * w;
-                                if (T > 0.5f) { median_depth = e.depth; median_contributor = contributor; }
-                                N0 += q3.x * w; N1 += q3.y * w; N2 += q3.z * w;
-                                C0 += q4.x * w; C1 += q4.y * w; C2 += q4.z * w;
-                                T = test_T;
-                                last_contributor = contributor;
-                            }
-                        }
+                        if (!eval_pair(pxf, pyf, q0, q1, q2, e)) continue;
+                        const float test_T = T * (1.0f - e.alpha);
+                        if (test_T < kTMin) { last_contributor |= 0x80000000u; break; }
+                        const uint32_t contributor = k32 - hb;   // 1-based list position
+                        const float4 q3 = lds128(ra + 3 * kBatch * 16), q4 = lds128(ra + 4 * kBatch * 16);
+                        const float w = e.alpha * T;
+                        const float A = 1.0f - T;
+                        const float mm = kMScale * (1.0f - kNear * fast_rcp(e.depth));
+                        dist += (mm * mm * A + M2 - 2.0f * mm * M1) * w;
+                        D += e.depth * w;
+                        M1 += mm * w;
+                        M2 += mm * mm * w;
+                        if (T > 0.5f) { median_depth = e.depth; median_contributor = contributor; }
+                        N0 += q3.x * w; N1 += q3.y * w; N2 += q3.z * w;
+                        C0 += q4.x * w; C1 += q4.y * w; C2 += q4.z * w;
+                        T = test_T;
+                        last_contributor = contributor;
                     }
                 }
-                if (__all_sync(0xffffffffu, done)) { warp_done = true; break; }
+                if (__all_sync(0xffffffffu, (int)last_contributor < 0)) { warp_done = true; break; }
             }
         }
     }
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(256, 5) render_fwd_kernel(RenderParams p) {
         const size_t HW = (size_t)p.H * p.W;
         const size_t pix = (size_t)py * p.W + px;
         p.accum[pix] = T; p.accum[HW + pix] = M1; p.accum[2 * HW + pix] = M2;
-        p.n_contrib[pix] = last_contributor; p.n_contrib[HW + pix] = median_contributor;
+        p.n_contrib[pix] = last_contributor & 0x7FFFFFFFu; p.n_contrib[HW + pix] = median_contributor;
         p.out_color[pix] = C0 + T * __ldg(p.bg + 0);
         p.out_color[HW + pix] = C1 + T * __ldg(p.bg + 1);
         p.out_color[2 * HW + pix] = C2 + T * __ldg(p.bg + 2);
