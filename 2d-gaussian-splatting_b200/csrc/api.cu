@@ -92,6 +92,23 @@ BinView bin_view(void* ws, size_t R, const Frame& f) {
     return v;
 }
 
+// Device-visible alias of a pinned (cudaHostAlloc / cudaHostRegister, mapped) host word, or nullptr.
+// One-entry cache: callers pass the same pinned word every step.
+uint32_t* mapped_alias(uint32_t* host) {
+    if (!host) return nullptr;
+    static thread_local uint32_t* last_host = nullptr;
+    static thread_local uint32_t* last_dev = nullptr;
+    if (host == last_host) return last_dev;
+    cudaPointerAttributes a;
+    uint32_t* dev = nullptr;
+    if (cudaPointerGetAttributes(&a, host) == cudaSuccess && a.type == cudaMemoryTypeHost && a.devicePointer)
+        dev = (uint32_t*)a.devicePointer;
+    else
+        (void)cudaGetLastError();
+    last_host = host; last_dev = dev;
+    return dev;
+}
+
 }  // namespace
 
 extern "C" {
@@ -178,8 +195,9 @@ int surfel_forward_preprocess(const surfel_settings_t* s, int P, int M, const fl
     p.offsets = (uint32_t*)(g + L.offsets); p.clamped = (uint8_t*)(g + L.clamped);
     p.scan_status = (unsigned long long*)(g + L.scan_status); p.counters = (uint32_t*)(g + L.counters);
     p.tile_count = image_ws ? (uint32_t*)((char*)image_ws + image_layout(f.W, f.H).tile_count) : nullptr;
+    p.num_rendered_mapped = mapped_alias(num_rendered_host);
     if (launch_preprocess_fwd(p, st)) return 1;
-    if (num_rendered_host)
+    if (num_rendered_host && !p.num_rendered_mapped)     // pageable / unmapped destination: copy engine
         SURFEL_CUDA_OK(cudaMemcpyAsync(num_rendered_host, p.counters + 1, 4, cudaMemcpyDeviceToHost, st));
     return 0;
 }

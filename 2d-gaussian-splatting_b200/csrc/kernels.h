@@ -15,6 +15,7 @@ struct PreFwdParams {
     int* radii; float4* rec; uint32_t* tiles_touched; uint32_t* offsets; uint8_t* clamped;
     unsigned long long* scan_status; uint32_t* counters;
     uint32_t* tile_count;   // optional (tiles): per-tile instance counts accumulated here (fused count)
+    uint32_t* num_rendered_mapped;   // optional: device-visible alias of the caller's pinned host word for R
 };
 
 struct PreBwdParams {

@@ -39,7 +39,10 @@ __device__ __forceinline__ bool eval_pair(float pxf, float pyf, const float4& q0
     const float ppx = __fmaf_rn(e.ky, e.lz, -__fmul_rn(e.kz, e.ly));
     const float ppy = __fmaf_rn(e.kz, e.lx, -__fmul_rn(e.kx, e.lz));
     e.pz = __fmaf_rn(e.kx, e.ly, -__fmul_rn(e.ky, e.lx));
-    if (e.pz == 0.0f) return false;
+    // The A.3 `continue` tests are folded into one predicate instead of four early exits: a warp
+    // practically never fails one of the first three on all 32 lanes, so as branches they only cost
+    // issue slots and branch-resolve stalls.  Lanes that fail keep computing on inf/NaN, harmlessly.
+    bool ok = e.pz != 0.0f;
     const float inv = fast_rcp(e.pz);
     e.inv_pz = inv;
     e.sx = __fmul_rn(ppx, inv); e.sy = __fmul_rn(ppy, inv);
@@ -49,13 +52,13 @@ __device__ __forceinline__ bool eval_pair(float pxf, float pyf, const float4& q0
     e.use3d = rho3d <= rho2d;
     const float rho = fminf(rho3d, rho2d);
     e.depth = e.use3d ? __fadd_rn(__fmaf_rn(e.sx, Twx, __fmul_rn(e.sy, Twy)), Twz) : Twz;
-    if (e.depth < kNear) return false;
+    ok &= !(e.depth < kNear);
     const float power = __fmul_rn(-0.5f, rho);
-    if (power > 0.0f) return false;
+    ok &= !(power > 0.0f);
     e.G = fast_ex2(__fmul_rn(power, 1.4426950408889634f));
     e.alpha = fminf(kAlphaMax, __fmul_rn(q2.w, e.G));
-    if (e.alpha < kAlphaMin) return false;
-    return true;
+    ok &= !(e.alpha < kAlphaMin);
+    return ok;
 }
 
 // Position of the highest set bit (FLO) and the mask of the bits below a position (BMSK): the hit

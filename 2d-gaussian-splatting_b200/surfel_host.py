@@ -37,17 +37,33 @@ class HostStepPipeline:
         self.done = torch.cuda.Event()
         self.n_in = 0
         self.n_comp = 0
+        self.trace = None        # profiling: list of (kind, step, start_event, end_event) when set to []
+
+    def _mark(self, stream):
+        if self.trace is None:
+            return None
+        e = torch.cuda.Event(enable_timing=True)
+        e.record(stream)
+        return e
+
+    def _close(self, kind, step, mark, stream):
+        if mark is not None:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            self.trace.append((kind, step, mark, e))
 
     def h2d(self, host_in, host_gc, host_go):
         """Enqueue the host->device copies of one step's inputs."""
         b = self.n_in % 2
         self.s_in.wait_event(self.free[b])            # compute that last read this buffer has finished
         with torch.cuda.stream(self.s_in):
+            mark = self._mark(self.s_in)
             for k in NAMES:
                 self.dev_in[b][k].copy_(host_in[k], non_blocking=True)
             self.dev_gc[b].copy_(host_gc, non_blocking=True)
             self.dev_go[b].copy_(host_go, non_blocking=True)
             self.ready[b].record(self.s_in)
+            self._close("h2d", self.n_in, mark, self.s_in)
         self.n_in += 1
 
     def compute_and_d2h(self, host_out, host_grad):
@@ -55,6 +71,7 @@ class HostStepPipeline:
         b = self.n_comp % 2
         with torch.cuda.stream(self.s_comp):
             self.s_comp.wait_event(self.ready[b])
+            mark = self._mark(self.s_comp)
             leaf = {k: self.dev_in[b][k].detach().requires_grad_(True) for k in NAMES}
             m2d = torch.zeros(self.P, 3, device=self.dev, requires_grad=True)
             color, radii, allmap = self.rast(means3D=leaf["means3D"], means2D=m2d, shs=leaf["shs"],
@@ -63,16 +80,19 @@ class HostStepPipeline:
             torch.autograd.backward([color, allmap], [self.dev_gc[b], self.dev_go[b]])
             self.done.record(self.s_comp)
             self.free[b].record(self.s_comp)
+            self._close("compute", self.n_comp, mark, self.s_comp)
         results = [("color", color.detach()), ("allmap", allmap.detach()), ("radii", radii)]
         grads = [(k, leaf[k].grad) for k in NAMES] + [("means2D", m2d.grad)]
         with torch.cuda.stream(self.s_out):
             self.s_out.wait_event(self.done)
+            mark = self._mark(self.s_out)
             for k, t in results:
                 t.record_stream(self.s_out)
                 host_out[k].copy_(t, non_blocking=True)
             for k, t in grads:
                 t.record_stream(self.s_out)
                 host_grad[k].copy_(t, non_blocking=True)
+            self._close("d2h", self.n_comp, mark, self.s_out)
         self.n_comp += 1
 
     def run(self, steps, host_in, host_gc, host_go, host_out, host_grad):

@@ -370,7 +370,7 @@ def run_ours(args, rank, local_rank, world):
         pipe = HostStepPipeline(rast, host_in, host_gc, host_go, dev)
         pipe.run(max(2, min(args.warmup, 3)), host_in, host_gc, host_go, host_out, host_grad)
         barrier()
-        e2e_steps = max(4, min(args.steps, 20))
+        e2e_steps = max(4, min(args.steps, 50))     # >= 4 so that the 3-stage pipeline reaches steady state
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ea.record(pipe.s_in)
         pipe.run(e2e_steps, host_in, host_gc, host_go, host_out, host_grad)

@@ -97,7 +97,9 @@ int surfel_image_offsets(int W, int H, size_t* out2);
 /* Forward, stage 1: preprocess every splat and scan tiles_touched.  Writes radii (P) int32 and the
  * geometry workspace.  If image_ws != NULL the per-tile instance counts are accumulated there in the
  * same launch (fused count for the tile-bucketed binning; pass tile_counts_ready = 1 downstream).  The instance count R is left in the workspace and, if
- * num_rendered_host != NULL (pinned host memory), copied there asynchronously on `stream`; the
+ * num_rendered_host != NULL, delivered there in stream order: for pinned, device-mapped host memory
+ * (cudaHostAlloc / torch pin_memory) the kernel stores it directly (no copy-engine transfer that
+ * could queue behind a bulk download on another stream); otherwise by a 4-byte cudaMemcpyAsync.  The
  * caller synchronises the stream (or an event) before reading it to size the binning workspace. */
 int surfel_forward_preprocess(const surfel_settings_t* s, int P, int M, const float* means3D,
                               const float* opacities, const float* scales, const float* rotations,
