@@ -30,6 +30,7 @@ SOURCES = {
     "render_bwd_tma.cu": [],
     "postprocess.cu": [],
     "loss.cu": [],
+    "optim.cu": [],
 }
 
 

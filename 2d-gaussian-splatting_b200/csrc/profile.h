@@ -7,7 +7,7 @@ namespace surfel {
 
 enum Stage { kStPreFwd = 0, kStDuplicate, kStSortHist, kStSortPass, kStRanges, kStRenderFwd,
              kStRenderBwd, kStPreBwd, kStMarkVisible, kStTileCount, kStTileScan, kStTileScatter,
-             kStTileSort, kNumStages };
+             kStTileSort, kStAdam, kStDensifyStats, kNumStages };
 
 void prof_count_launch();
 bool prof_enabled();

@@ -25,6 +25,15 @@ class SurfelSettings(ctypes.Structure):
     ]
 
 
+class AdamGroup(ctypes.Structure):
+    """struct surfel_adam_group (include/surfel_rasterizer.h)."""
+    _fields_ = [("param", c_void_p), ("grad", c_void_p), ("exp_avg", c_void_p), ("exp_avg_sq", c_void_p),
+                ("n", ctypes.c_longlong), ("step_size", c_float), ("bias2_sqrt", c_float),
+                ("aligned16", ctypes.c_int)]
+
+
+ADAM_MAX_GROUPS = 8
+
 # name -> (restype, argtypes); every symbol include/surfel_rasterizer.h declares
 SIGNATURES = {
     "surfel_abi_version": (c_int, []),
@@ -52,6 +61,8 @@ SIGNATURES = {
     "surfel_post_backward": (c_int, [c_int, c_int, c_float] + [c_void_p] * 9 + [c_void_p]),
     "surfel_l1_ssim_forward": (c_int, [c_int, c_int, c_int] + [c_void_p] * 6 + [c_void_p]),
     "surfel_l1_ssim_backward": (c_int, [c_int, c_int, c_int] + [c_void_p] * 7 + [c_void_p]),
+    "surfel_adam_step": (c_int, [c_int, ctypes.POINTER(AdamGroup), ctypes.c_double, ctypes.c_double, ctypes.c_double, c_void_p]),
+    "surfel_densify_stats": (c_int, [c_int] + [c_void_p] * 5 + [c_void_p]),
     "surfel_launch_count": (ctypes.c_ulonglong, []),
     "surfel_profile_enable": (None, [c_int]),
     "surfel_profile_num_stages": (c_int, []),

@@ -180,6 +180,33 @@ int surfel_l1_ssim_backward(int C, int H, int W, const float* img, const float* 
                             const float* ds11, const float* ds12, const float* gscale2, float* g_img,
                             void* stream);
 
+/* ---- the parameter update after the backward -------------------------------
+ * surfel_adam_step replaces torch.optim.Adam(l, lr=0.0, eps=1e-15).step() of the reference
+ * (/root/reference/scene/gaussian_model.py:148-166, /root/reference/train.py:138-140): ONE launch
+ * updates every parameter group in place (param, exp_avg, exp_avg_sq), arithmetic as torch's
+ * single-tensor Adam (no weight decay, no amsgrad).  The host folds the step count into
+ *   step_size = lr / (1 - beta1^step),   bias2_sqrt = sqrt(1 - beta2^step)
+ * (in double, as torch does); betas and eps are doubles so that 1 - beta is rounded once.
+ * surfel_densify_stats replaces /root/reference/train.py:125-128 (max_radii2D update) and
+ * /root/reference/scene/gaussian_model.py:405-407 (add_densification_stats): where radii > 0,
+ *   max_radii2D = max(max_radii2D, radii); xyz_gradient_accum += |means2D_grad (3)|; denom += 1.
+ * max_radii2D may be NULL. */
+#define SURFEL_ADAM_MAX_GROUPS 8
+typedef struct surfel_adam_group {
+    float* param;            /* n floats, updated in place */
+    const float* grad;       /* n floats */
+    float* exp_avg;          /* n floats, updated in place */
+    float* exp_avg_sq;       /* n floats, updated in place */
+    long long n;
+    float step_size;
+    float bias2_sqrt;
+    int aligned16;           /* filled in by the library */
+} surfel_adam_group_t;
+int surfel_adam_step(int n_groups, const surfel_adam_group_t* groups, double beta1, double beta2, double eps,
+                     void* stream);
+int surfel_densify_stats(int P, const int32_t* radii, const float* means2D_grad, float* xyz_gradient_accum,
+                         float* denom, float* max_radii2D, void* stream);
+
 /* Instrumentation used by bench.py: number of kernels this library has launched in this process,
  * and optional per-stage CUDA-event timing (events recorded on the launching stream around each
  * kernel while enabled; surfel_profile_read() waits for them and returns summed ms / launch counts
