@@ -23,6 +23,13 @@ __constant__ float b_SH_C3[7] = {-0.5900435899266435f, 2.890611442640554f, -0.45
 constexpr float SH_C0 = 0.28209479177387814f;
 constexpr float SH_C1 = 0.4886025119029199f;
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 constexpr int kRowQuads = 13;   // 12 data quads + 1 pad: conflict-free 128-bit row access
 
 // kStaged: SH rows (in) and dL_dsh rows (out) travel through shared memory so that every global
@@ -44,6 +51,30 @@ __global__ void __launch_bounds__(128, 6) preprocess_bwd_kernel(PreBwdParams p) 
     float tm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     float g3[3] = {0, 0, 0}, gs[2] = {0, 0}, gq[4] = {0, 0, 0, 0};
     float px = 0, py = 0, pz = 0;
+
+    // Every input of the splat is requested in the first round trip to HBM: the SH rows by cp.async
+    // (LDGSTS) straight into the warp's panel, position / rotation / scale into registers, while the
+    // gradient record and the forward record are fetched and the homography vjp is computed.
+    const unsigned vis_mask = kStaged ? __ballot_sync(0xffffffffu, visible) : 0u;
+    if (kStaged && has_sh && vis_mask) {
+        const float4* src = reinterpret_cast<const float4*>(p.shs) + (size_t)(blockIdx.x * blockDim.x + warp * 32) * 12;
+        float4* dst = s_rows + warp * 32 * kRowQuads;
+#pragma unroll
+        for (int it = 0; it < 12; it++) {
+            const int f = it * 32 + lane;
+            const int row = f / 12, q = f - row * 12;
+            if ((vis_mask >> row) & 1u) cp_async16(dst + row * kRowQuads + q, src + f);
+        }
+    }
+    float4 rot_in = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+    float2 scale_in = make_float2(0.0f, 0.0f);
+    if (visible) {
+        px = p.means3D[3 * (size_t)idx]; py = p.means3D[3 * (size_t)idx + 1]; pz = p.means3D[3 * (size_t)idx + 2];
+        if (geom) {
+            rot_in = reinterpret_cast<const float4*>(p.rotations)[idx];
+            scale_in = reinterpret_cast<const float2*>(p.scales)[idx];
+        }
+    }
 
     if (visible) {
         const float4* gr = reinterpret_cast<const float4*>(p.grad_rec + (size_t)idx * kGradFloats);
@@ -94,14 +125,13 @@ __global__ void __launch_bounds__(128, 6) preprocess_bwd_kernel(PreBwdParams p) 
             for (int k = 0; k < 3; k++) gT[6 + k] += dT3[k] + dL_dd * (t[k] * tm[6 + k] * 2.0f);
         }
 
-        px = p.means3D[3 * (size_t)idx]; py = p.means3D[3 * (size_t)idx + 1]; pz = p.means3D[3 * (size_t)idx + 2];
         if (geom) {
             const float* vm = p.viewmatrix;
             const float* pr = p.projmatrix;
             const float hw = (float)p.W / 2.0f, hh = (float)p.H / 2.0f;
             const float cw = (float)(p.W - 1) / 2.0f, ch = (float)(p.H - 1) / 2.0f;
-            const float4 q = reinterpret_cast<const float4*>(p.rotations)[idx];
-            const float2 sc = reinterpret_cast<const float2*>(p.scales)[idx];
+            const float4 q = rot_in;
+            const float2 sc = scale_in;
             const float inv = 1.0f / sqrtf(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
             const float w = q.x * inv, x = q.y * inv, y = q.z * inv, z = q.w * inv;
             float R[3][3];
@@ -152,14 +182,8 @@ __global__ void __launch_bounds__(128, 6) preprocess_bwd_kernel(PreBwdParams p) 
         float4* wrow = s_rows + (kStaged ? (warp * 32 + lane) * kRowQuads : 0);
         const int warp_first = blockIdx.x * blockDim.x + warp * 32;
         if (kStaged) {
-            // cooperative, fully coalesced load of the warp's 32 SH rows (only rows of visible splats)
-            const unsigned vis_mask = __ballot_sync(0xffffffffu, visible);
-            const float4* src = reinterpret_cast<const float4*>(p.shs) + (size_t)warp_first * 12;
-            float4* dst = s_rows + warp * 32 * kRowQuads;
-            for (int f = lane; f < 32 * 12; f += 32) {
-                const int row = f / 12, q = f - row * 12;
-                if ((vis_mask >> row) & 1u) dst[row * kRowQuads + q] = ld_nc_f4(src + f);
-            }
+            // the warp's SH rows (only rows of visible splats) were requested at the top of the kernel
+            cp_async_wait_all();
             __syncwarp();
             if (visible) {
 #pragma unroll

@@ -9,7 +9,8 @@
 // inclusive offsets and the instance count R come out of the same launch (no separate scan
 // kernel, no second pass over tiles_touched).
 //
-// B200 notes: SH rows (192 B/splat, AoS) are the dominant HBM stream.  Only rows of splats that
+// B200 notes: SH rows (192 B/splat, AoS) are the dominant HBM stream; with the vectorised layout they are
+// prefetched by cp.async (LDGSTS) while the geometry is computed.  Only rows of splats that
 // survive culling are fetched, warp-cooperatively with 128-bit loads into padded shared memory
 // (conflict-free 13-quad stride), instead of upstream's per-thread stride-192 scalar reads.
 //
@@ -64,6 +65,15 @@ __device__ __forceinline__ float sh_eval_channel(const float* sh, int c, int D, 
     return r;
 }
 
+// 16-byte global -> shared copy that bypasses registers and L1 (LDGSTS): the SH rows are fetched while
+// the geometry of the same splats is being computed.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
 constexpr int kShRowQuads = 13;                 // 12 data quads + 1 pad: conflict-free LDS.128
 constexpr int kShRowFloatsScalar = 49;          // scalar path stride (odd: conflict-free LDS.32)
 
@@ -85,23 +95,63 @@ __global__ void __launch_bounds__(kPreBlock, 8) preprocess_fwd_kernel(PreFwdPara
     int rx0 = 0, ry0 = 0, rw = 1;
     float tm[9], nrm[3] = {0, 0, 0}, cx = 0, cy = 0, pvz = 0, opa = 0;
     int radius_i = 0;
-    float px = 0, py = 0, pz = 0;
+    float px = 0, py = 0, pz = 0, pvx = 0, pvy = 0, opa_in = 0;
+    float4 rot_in = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+    float2 scale_in = make_float2(0.0f, 0.0f);
     const float* vm = p.viewmatrix;
 
     if (idx < p.P) {
         px = p.means3D[3 * (size_t)idx + 0];
         py = p.means3D[3 * (size_t)idx + 1];
         pz = p.means3D[3 * (size_t)idx + 2];
-        const float pvx = ((vm[0] * px + vm[4] * py) + vm[8] * pz) + vm[12];
-        const float pvy = ((vm[1] * px + vm[5] * py) + vm[9] * pz) + vm[13];
+        // every per-splat input is requested in the same round trip as the position (a culled splat
+        // wastes 28 bytes; a visible one saves two dependent trips to HBM)
+        if (p.transMat_precomp == nullptr) {
+            rot_in = reinterpret_cast<const float4*>(p.rotations)[idx];
+            scale_in = reinterpret_cast<const float2*>(p.scales)[idx];
+        }
+        opa_in = p.opacities[idx];
+        pvx = ((vm[0] * px + vm[4] * py) + vm[8] * pz) + vm[12];
+        pvy = ((vm[1] * px + vm[5] * py) + vm[9] * pz) + vm[13];
         pvz = ((vm[2] * px + vm[6] * py) + vm[10] * pz) + vm[14];
+    }
+    // ---- SH prefetch (vectorised layout only).  The rows of splats that pass the near plane and whose
+    // centre projects within 1.5x the screen are requested NOW with cp.async and land in the warp's
+    // panel while T / AABB / tile counts / the scan are computed; whatever turns out visible without
+    // having been requested (huge off-screen splats) is fetched later by the plain path.  Only the
+    // data movement changes: the arithmetic below is untouched. ----
+    unsigned prefetched = 0;
+    if (kVec4) {
+        bool cand = false;
+        if (idx < p.P && pvz > kNear) {
+            const float* pr = p.projmatrix;
+            const float hx = ((pr[0] * px + pr[4] * py) + pr[8] * pz) + pr[12];
+            const float hy = ((pr[1] * px + pr[5] * py) + pr[9] * pz) + pr[13];
+            const float hw4 = ((pr[3] * px + pr[7] * py) + pr[11] * pz) + pr[15];
+            const float lim = 1.5f * fabsf(hw4);
+            cand = fabsf(hx) <= lim && fabsf(hy) <= lim;
+        }
+        prefetched = __ballot_sync(0xffffffffu, cand);
+        if (prefetched) {
+            const int warp_base = (int)(bid * kPreBlock) + warp * 32;
+            float4* dst = s_sh + warp * 32 * kShRowQuads;
+            const float4* src = reinterpret_cast<const float4*>(p.shs) + (size_t)warp_base * 12;
+#pragma unroll
+            for (int it = 0; it < 12; it++) {
+                const int f = it * 32 + lane;              // quad f of the warp's contiguous 6 KB of SH
+                const int row = f / 12, q = f - row * 12;
+                if ((prefetched >> row) & 1u) cp_async16(dst + row * kShRowQuads + q, src + f);
+            }
+        }
+    }
+    if (idx < p.P) {
         if (pvz > kNear) {
             // per-view Pm = projmatrix * ndc2pix (columns x*w, y*w, w)
             const float hw = (float)p.W / 2.0f, hh = (float)p.H / 2.0f;
             const float cw = (float)(p.W - 1) / 2.0f, ch = (float)(p.H - 1) / 2.0f;
             if (p.transMat_precomp == nullptr) {
-                const float4 q = reinterpret_cast<const float4*>(p.rotations)[idx];
-                const float2 sc = reinterpret_cast<const float2*>(p.scales)[idx];
+                const float4 q = rot_in;
+                const float2 sc = scale_in;
                 const float n2 = ((q.x * q.x + q.y * q.y) + q.z * q.z) + q.w * q.w;
                 const float inv = 1.0f / sqrtf(n2);
                 const float w = q.x * inv, x = q.y * inv, y = q.z * inv, z = q.w * inv;
@@ -163,7 +213,7 @@ __global__ void __launch_bounds__(kPreBlock, 8) preprocess_fwd_kernel(PreFwdPara
                 }
             }
         }
-        if (visible) opa = p.opacities[idx];
+        if (visible) opa = opa_in;
     }
 
     // ---- fused per-tile instance count for the tile-bucketed binning (bucket_sort.cu): small rects
@@ -211,6 +261,7 @@ __global__ void __launch_bounds__(kPreBlock, 8) preprocess_fwd_kernel(PreFwdPara
     float rgb[3] = {0, 0, 0};
     unsigned clamp_bits = 0;
     const unsigned vis_mask = __ballot_sync(0xffffffffu, visible);
+    if (kVec4) cp_async_wait_all();      // this lane's prefetched quads have landed (made visible to the warp below)
     if (p.colors_precomp == nullptr) {
         if (vis_mask) {
             int* rows = s_rows + warp * 32;
@@ -222,10 +273,11 @@ __global__ void __launch_bounds__(kPreBlock, 8) preprocess_fwd_kernel(PreFwdPara
             if (kVec4) {
                 float4* dst = s_sh + warp * 32 * kShRowQuads;
                 const float4* src = reinterpret_cast<const float4*>(p.shs);
-                for (int f = lane; f < nvis * 12; f += 32) {
-                    const int slot = f / 12, q = f - slot * 12;
-                    const int row = rows[slot];
-                    dst[row * kShRowQuads + q] = ld_nc_f4(src + (size_t)(warp_base + row) * 12 + q);
+                unsigned missing = vis_mask & ~prefetched;     // visible but not requested up front (rare)
+                while (missing) {
+                    const int row = __ffs(missing) - 1;
+                    missing &= missing - 1;
+                    if (lane < 12) dst[row * kShRowQuads + lane] = ld_nc_f4(src + (size_t)(warp_base + row) * 12 + lane);
                 }
                 __syncwarp();
                 if (visible) {
