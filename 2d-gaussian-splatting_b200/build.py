@@ -31,6 +31,7 @@ SOURCES = {
     "postprocess.cu": [],
     "loss.cu": [],
     "optim.cu": [],
+    "ply_pack.cu": [],
 }
 
 

@@ -61,7 +61,7 @@ const char* surfel_profile_stage_name(int stage) {
     static const char* names[kNumStages] = {"preprocess_fwd", "duplicate_with_keys", "sort_histogram",
                                             "sort_onesweep_pass", "identify_tile_ranges", "render_fwd",
                                             "render_bwd", "preprocess_bwd", "mark_visible", "tile_count", "tile_scan",
-                                            "tile_scatter", "tile_sort", "adam_step", "densify_stats"};
+                                            "tile_scatter", "tile_sort", "adam_step", "densify_stats", "ply_unpack", "ply_pack"};
     return stage >= 0 && stage < kNumStages ? names[stage] : "";
 }
 int surfel_profile_read(double* ms_out, int* count_out) {

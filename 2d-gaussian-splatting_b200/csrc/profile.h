@@ -7,7 +7,7 @@ namespace surfel {
 
 enum Stage { kStPreFwd = 0, kStDuplicate, kStSortHist, kStSortPass, kStRanges, kStRenderFwd,
              kStRenderBwd, kStPreBwd, kStMarkVisible, kStTileCount, kStTileScan, kStTileScatter,
-             kStTileSort, kStAdam, kStDensifyStats, kNumStages };
+             kStTileSort, kStAdam, kStDensifyStats, kStPlyUnpack, kStPlyPack, kNumStages };
 
 void prof_count_launch();
 bool prof_enabled();

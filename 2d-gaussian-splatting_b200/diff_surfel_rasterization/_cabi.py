@@ -63,6 +63,8 @@ SIGNATURES = {
     "surfel_l1_ssim_backward": (c_int, [c_int, c_int, c_int] + [c_void_p] * 7 + [c_void_p]),
     "surfel_adam_step": (c_int, [c_int, ctypes.POINTER(AdamGroup), ctypes.c_double, ctypes.c_double, ctypes.c_double, c_void_p]),
     "surfel_densify_stats": (c_int, [c_int] + [c_void_p] * 5 + [c_void_p]),
+    "surfel_ply_unpack": (c_int, [c_int, c_int, c_void_p, ctypes.POINTER(ctypes.c_int32), c_int] + [c_void_p] * 5 + [c_void_p]),
+    "surfel_ply_pack": (c_int, [c_int] + [c_void_p] * 7 + [c_void_p]),
     "surfel_launch_count": (ctypes.c_ulonglong, []),
     "surfel_profile_enable": (None, [c_int]),
     "surfel_profile_num_stages": (c_int, []),

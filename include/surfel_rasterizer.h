@@ -207,6 +207,27 @@ int surfel_adam_step(int n_groups, const surfel_adam_group_t* groups, double bet
 int surfel_densify_stats(int P, const int32_t* radii, const float* means2D_grad, float* xyz_gradient_accum,
                          float* denom, float* max_radii2D, void* stream);
 
+/* ---- the model's on-disk format either side of the path ------------------
+ * The reference saves / loads a trained model as a binary little-endian PLY with one row of 61
+ * float32 per splat, pre-activation, SH channel-major (/root/reference/scene/gaussian_model.py:176-209
+ * save_ply, :215-255 load_ply):  x y z nx ny nz f_dc_0..2 f_rest_0..44 opacity scale_0..1 rot_0..3.
+ * surfel_ply_unpack turns raw rows (device memory, `row_floats` floats each, any property order)
+ * into the rasterizer's inputs in one pass.  columns[58] gives, for every target float, its column
+ * in the row; target order: 0..2 xyz | 3..50 shs[k][c] (coefficient-major (16,3): k = 0 is f_dc_c,
+ * k >= 1 is f_rest_{c*15 + k-1}) | 51 opacity | 52..53 scale | 54..57 rot (w,x,y,z).
+ * activate = 1 applies what the reference's getters apply before the op (gaussian_model.py:35-41,
+ * :95-115): opacity = sigmoid, scale = exp, rot = q / max(|q|, 1e-12); activate = 0 leaves the
+ * stored parameters.  surfel_ply_pack is the inverse of save_ply's gather: parameters
+ * (xyz (P,3), features_dc (P,1,3), features_rest (P,15,3), opacity (P,1), scaling (P,2),
+ * rotation (P,4)) -> rows in the reference's column order with zero normals. */
+#define SURFEL_PLY_ROW_FLOATS 61
+#define SURFEL_PLY_TARGETS 58
+#define SURFEL_PLY_MAX_ROW_FLOATS 127
+int surfel_ply_unpack(int P, int row_floats, const float* rows, const int32_t* columns, int activate,
+                      float* means3D, float* shs, float* opacities, float* scales, float* rotations, void* stream);
+int surfel_ply_pack(int P, const float* xyz, const float* features_dc, const float* features_rest,
+                    const float* opacity, const float* scaling, const float* rotation, float* rows, void* stream);
+
 /* Instrumentation used by bench.py: number of kernels this library has launched in this process,
  * and optional per-stage CUDA-event timing (events recorded on the launching stream around each
  * kernel while enabled; surfel_profile_read() waits for them and returns summed ms / launch counts
