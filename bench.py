@@ -219,7 +219,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference CUDA rasterizer is not vendored in /root/reference; this is the CPU restatement (oracle/)",
     }
-    print(json.dumps(out))
+    _emit(json.dumps(out))
 
 
 def run_ours(args, rank, local_rank, world):
@@ -428,7 +428,32 @@ def run_ours(args, rank, local_rank, world):
         }
         if cpu_baseline is not None:
             out["cpu_baseline"] = cpu_baseline
-        print(json.dumps(out))
+        _emit(json.dumps(out))
+
+
+class _CleanStdout:
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its
+    version banner when NCCL_DEBUG is set, OpenMP runtimes warn, ...), so for the duration of the run file
+    descriptor 1 points at stderr and the JSON line is written to the saved, real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.real, (line.rstrip("\n") + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+        return False
+
+
+_emit = print          # replaced by _CleanStdout.emit while main() runs
 
 
 def main():
@@ -446,20 +471,26 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-        return
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    try:
-        run_ours(args, rank, local_rank, world)
-    finally:
-        if world > 1:
-            import torch.distributed as dist
-            dist.destroy_process_group()
+    global _emit
+    with _CleanStdout() as out:
+        _emit = out.emit
+        try:
+            if args.impl == "reference":
+                run_reference(args, rank, world)
+                return
+            if world > 1:
+                import torch
+                import torch.distributed as dist
+                torch.cuda.set_device(local_rank)
+                dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            try:
+                run_ours(args, rank, local_rank, world)
+            finally:
+                if world > 1:
+                    import torch.distributed as dist
+                    dist.destroy_process_group()
+        finally:
+            _emit = print
 
 
 if __name__ == "__main__":
