@@ -92,21 +92,16 @@ BinView bin_view(void* ws, size_t R, const Frame& f) {
     return v;
 }
 
-// Device-visible alias of a pinned (cudaHostAlloc / cudaHostRegister, mapped) host word, or nullptr.
-// One-entry cache: callers pass the same pinned word every step.
+// Device-visible alias of a pinned (cudaHostAlloc / cudaHostRegister, mapped) host word, or nullptr
+// for pageable memory.  Queried on every call (about a microsecond): a cached answer could outlive
+// the allocation it described.
 uint32_t* mapped_alias(uint32_t* host) {
     if (!host) return nullptr;
-    static thread_local uint32_t* last_host = nullptr;
-    static thread_local uint32_t* last_dev = nullptr;
-    if (host == last_host) return last_dev;
     cudaPointerAttributes a;
-    uint32_t* dev = nullptr;
     if (cudaPointerGetAttributes(&a, host) == cudaSuccess && a.type == cudaMemoryTypeHost && a.devicePointer)
-        dev = (uint32_t*)a.devicePointer;
-    else
-        (void)cudaGetLastError();
-    last_host = host; last_dev = dev;
-    return dev;
+        return (uint32_t*)a.devicePointer;
+    (void)cudaGetLastError();
+    return nullptr;
 }
 
 }  // namespace
