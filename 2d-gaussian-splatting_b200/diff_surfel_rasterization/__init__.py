@@ -23,6 +23,8 @@ CPU tensor raises.
 """
 import ctypes
 import os
+import threading
+import time
 from typing import NamedTuple, Optional, Tuple
 
 import torch
@@ -35,6 +37,25 @@ __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gau
 # Recalled upstream behaviour in the low-pass branch of the render backward that is NOT the
 # derivative of the forward (adds s.x*dL_dz, s.y*dL_dz to dL_dTw.xy).  Off by default; see DESIGN.md.
 LOWPASS_DEPTH_QUIRK = bool(int(os.environ.get("SURFEL_LOWPASS_DEPTH_QUIRK", "0")))
+
+# Optional host-side trace (profiles/host_trace.py): when switched on, the autograd node appends
+# (tag, perf_counter_ns, thread id) at the points that bound the host's critical sections — between
+# "R is known" and "backward is launched", and between "backward is launched" and "next preprocess is
+# launched".  Off by default: one `is not None` test per mark.
+_TRACE = None
+
+
+def trace_host(on):
+    """Start (True) / stop (False) the host trace; returns the list of marks collected so far."""
+    global _TRACE
+    old = _TRACE
+    _TRACE = [] if on else None
+    return old
+
+
+def _mark(tag):
+    if _TRACE is not None:
+        _TRACE.append((tag, time.perf_counter_ns(), threading.get_ident()))
 
 
 class GaussianRasterizationSettings(NamedTuple):
@@ -128,6 +149,7 @@ class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                 cov3Ds_precomp, raster_settings):
+        _mark("fwd_enter")
         lib = _cabi.load()
         rs = raster_settings
         if means3D.dim() != 2 or means3D.shape[1] != 3:
@@ -163,6 +185,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                     _ptr(rotations), _ptr(cov3Ds_precomp), _ptr(sh), _ptr(colors_precomp),
                     radii.data_ptr(), geom.data_ptr(), img.data_ptr(), host_R.data_ptr(), stream))
                 ev.record(torch.cuda.current_stream(dev))
+                _mark("preprocess_launched")
                 # The instance count R sizes the binning workspace, so upstream blocks here until the
                 # device has produced it.  We launch binning + render SPECULATIVELY with the capacity
                 # remembered from earlier calls of the same shape (every kernel clamps to it), and only
@@ -190,7 +213,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                         d_scales=e(P, 2) if scales is not None else None,
                         d_rot=e(P, 4) if scales is not None else None,
                         scratch=e(max(P, 1), lib.surfel_grad_scratch_floats()))
+                _mark("speculative_work_launched")
                 ev.synchronize()
+                _mark("R_known")
                 R = int(host_R.item()) & 0xFFFFFFFF
                 if R > cap or not cap:
                     cap = R if not spec else int(R * 1.25) + 4096
@@ -214,10 +239,12 @@ class _RasterizeGaussians(torch.autograd.Function):
                               none if cov3Ds_precomp is None else cov3Ds_precomp,
                               none if sh is None else sh, radii, geom, binning, img)
         ctx.mark_non_differentiable(radii)
+        _mark("fwd_exit")
         return color, radii, allmap
 
     @staticmethod
     def backward(ctx, grad_color, grad_radii, grad_allmap):
+        _mark("bwd_enter")
         lib = _cabi.load()
         rs = ctx.raster_settings
         means3D, scales, rotations, cov3Ds, sh, radii, geom, binning, img = ctx.saved_tensors
@@ -250,6 +277,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 img.data_ptr(), g_color.data_ptr(), g_all.data_ptr(), scratch.data_ptr(),
                 d_means2D.data_ptr(), _ptr(d_colors), d_opacity.data_ptr(), d_means3D.data_ptr(),
                 _ptr(d_cov), _ptr(d_sh), _ptr(d_scales), _ptr(d_rot), int(LOWPASS_DEPTH_QUIRK), stream))
+        _mark("bwd_launched")
         # (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, settings)
         return d_means3D, d_means2D, d_sh, d_colors, d_opacity, d_scales, d_rot, d_cov, None
 
