@@ -95,3 +95,43 @@ def test_no_cpu_path(tmp_path):
         PLY.load_ply(str(path), device="cpu")
     with pytest.raises(RuntimeError, match="no CPU path"):
         PLY.unpack_rows(torch.zeros(3, 61), PLY.reference_attributes(), True)
+
+
+# ---- pinned to the reference's own save_ply / load_ply (tests/golden/make_golden_ply.py) ----
+
+def _gold():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_ply.npz"))
+
+
+def test_attribute_order_is_the_references():
+    g = _gold()
+    assert [str(n) for n in g["names"]] == PLY.reference_attributes()
+
+
+def test_row_assembly_matches_reference_save_ply():
+    """reference_file_bytes (the oracle of the byte-identity GPU test) assembles rows exactly like save_ply."""
+    g = _gold()
+    blob = reference_file_bytes(g["xyz"], g["features_dc"], g["features_rest"], g["opacity"], g["scaling"], g["rotation"])
+    count, names, offset = PLY.parse_header(blob)
+    rows = np.frombuffer(blob, dtype="<f4", offset=offset).reshape(count, len(names))
+    assert count == g["rows"].shape[0] and np.array_equal(rows, g["rows"])
+
+
+def test_column_table_reproduces_reference_load_ply():
+    """Gathering the golden rows through column_table gives the tensors load_ply builds (features in the
+    (P,16,3) layout = cat(_features_dc, _features_rest)), and the activations are the getters'."""
+    import torch
+    g = _gold()
+    cols = PLY.column_table([str(n) for n in g["names"]])
+    t = g["rows"][:, cols]                                     # (P, 58) in surfel_ply_unpack's target order
+    assert np.array_equal(t[:, 0:3], g["loaded_xyz"])
+    shs = t[:, 3:51].reshape(-1, 16, 3)
+    assert np.array_equal(shs[:, :1], g["loaded_features_dc"]) and np.array_equal(shs[:, 1:], g["loaded_features_rest"])
+    assert np.array_equal(shs, g["act_features"])
+    assert np.array_equal(t[:, 51:52], g["loaded_opacity"]) and np.array_equal(t[:, 52:54], g["loaded_scaling"])
+    assert np.array_equal(t[:, 54:58], g["loaded_rotation"])
+    # what activate=1 must produce (gaussian_model.py getters), here with torch on CPU
+    np.testing.assert_allclose(torch.sigmoid(torch.from_numpy(t[:, 51:52])).numpy(), g["act_opacity"], rtol=1e-6)
+    np.testing.assert_allclose(np.exp(t[:, 52:54]), g["act_scaling"], rtol=1e-6)
+    np.testing.assert_allclose(torch.nn.functional.normalize(torch.from_numpy(t[:, 54:58])).numpy(), g["act_rotation"], rtol=1e-6)
