@@ -141,12 +141,8 @@ int surfel_ply_unpack(int P, int row_floats, const float* rows, const int32_t* c
         t.col[i] = columns[i];
     }
     const size_t smem = (size_t)4 * 32 * (row_floats | 1) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        SURFEL_CUDA_OK(cudaFuncSetAttribute(ply_unpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            4 * 32 * (kPlyMaxRow | 1) * (int)sizeof(float)));
-        attr_set = true;
-    }
+    if (smem > 48 * 1024)       // rows wider than 95 floats (never the reference's 61): opt in per launch; the attribute is per device
+        SURFEL_CUDA_OK(cudaFuncSetAttribute(ply_unpack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LaunchScope scope(kStPlyUnpack, (cudaStream_t)stream);
     ply_unpack_kernel<<<(P + 127) / 128, 128, smem, (cudaStream_t)stream>>>(P, row_floats, rows, t, activate, means3D,
                                                                            shs, opacities, scales, rotations);

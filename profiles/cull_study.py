@@ -74,7 +74,8 @@ def main():
             hx, hy = np.sqrt(C / (A * C - B * B)), np.sqrt(A / (A * C - B * B))      # AABB half extents
             bx0, bx1 = min(cx - r, ex - hx - f32(0.05)), max(cx + r, ex + hx + f32(0.05))
             by0, by1 = min(cy - r, ey - hy - f32(0.05)), max(cy + r, ey + hy + f32(0.05))
-        else:
+            bounded = bool(np.isfinite([bx0, bx1, by0, by1]).all())
+        if not bounded:
             n_unbounded += 1
             continue                                          # never culled today either
         x0, x1 = max(0, int(np.ceil(bx0))), min(W - 1, int(np.floor(bx1)))
