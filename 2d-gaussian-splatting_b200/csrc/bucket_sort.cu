@@ -450,11 +450,12 @@ int launch_bucket_binning(int P, size_t R, int gx, int gy, int row0, int row1, c
         SURFEL_CUDA_OK(cudaGetLastError());
     }
     {
-        static bool attr_set = false;
-        if (!attr_set) {
+        static bool attr_set[kMaxDevices] = {};
+        const int slot = current_device_slot();
+        if (slot < 0 || !attr_set[slot]) {
             SURFEL_CUDA_OK(cudaFuncSetAttribute(tile_sort_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                 kLargeMax * 8));
-            attr_set = true;
+            if (slot >= 0) attr_set[slot] = true;
         }
         LaunchScope scope(kStTileSort, stream);
         tile_sort_large_kernel<<<148, 1024, kLargeMax * 8, stream>>>(ranges, pairs, point_list, keys_sorted, big_list, big_count);

@@ -112,6 +112,16 @@ __device__ __forceinline__ float4 ld_nc_f4(const float4* p) {
 
 // Error plumbing shared by the C-ABI translation units.
 void surfel_set_error(const char* fmt, ...);
+
+// Per-device one-time initialisation (function attributes and __constant__ tables live per device, and a
+// process may drive several): slot of the current device in a caller-owned `static bool done[kMaxDevices]`,
+// or -1 if it cannot be determined (then the caller initialises again; all such initialisations are idempotent).
+constexpr int kMaxDevices = 64;
+inline int current_device_slot() {
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return -1;
+    return dev;
+}
 #define SURFEL_CUDA_OK(expr)                                                              \
     do {                                                                                  \
         cudaError_t _e = (expr);                                                          \

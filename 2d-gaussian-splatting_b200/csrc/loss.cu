@@ -138,14 +138,15 @@ int surfel_l1_ssim_forward(int C, int H, int W, const float* img, const float* g
                            float* ds11, float* ds12, double* sums2, void* stream) {
     if (C <= 0 || H <= 0 || W <= 0) { surfel_set_error("surfel_l1_ssim_forward: bad shape"); return 1; }
     cudaStream_t st = (cudaStream_t)stream;
-    static bool init = false;
-    if (!init) {
+    static bool init[kMaxDevices] = {};                 // the window lives in __constant__ memory: one copy per device
+    const int slot = current_device_slot();
+    if (slot < 0 || !init[slot]) {
         // same construction as the reference: exp(-(x-5)^2 / (2*1.5^2)) as float32, normalised in float32
         float g[kWin], s = 0.0f;
         for (int i = 0; i < kWin; i++) { g[i] = (float)exp(-(double)((i - kHalfW) * (i - kHalfW)) / (2.0 * 1.5 * 1.5)); s += g[i]; }
         for (int i = 0; i < kWin; i++) g[i] /= s;
         SURFEL_CUDA_OK(cudaMemcpyToSymbol(c_gauss, g, sizeof(g)));
-        init = true;
+        if (slot >= 0) init[slot] = true;
     }
     SURFEL_CUDA_OK(cudaMemsetAsync(sums2, 0, 2 * sizeof(double), st));
     dim3 grid((W + kLT - 1) / kLT, (H + kLT - 1) / kLT, C), blk(kLT, kLT);

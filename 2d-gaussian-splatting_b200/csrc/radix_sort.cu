@@ -250,12 +250,13 @@ int launch_radix_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b
     SURFEL_CUDA_OK(cudaMemsetAsync(t.tickets, 0, 256, stream));
     SURFEL_CUDA_OK(cudaMemsetAsync(t.status, 0, (size_t)passes * tiles * kRadix * 4, stream));
 
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[kMaxDevices] = {};
+    const int slot = current_device_slot();
+    if (slot < 0 || !attr_set[slot]) {
         SURFEL_CUDA_OK(cudaFuncSetAttribute(radix_onesweep_kernel,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)sizeof(SortSmem)));
-        attr_set = true;
+        if (slot >= 0) attr_set[slot] = true;
     }
     const int hist_blocks = (int)std::min((size_t)148 * 8, (n + 255) / 256);
     { LaunchScope scope(kStSortHist, stream);
