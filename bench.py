@@ -284,9 +284,11 @@ def run_ours(args, rank, local_rank, world):
     launches0 = lib.surfel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler.mark_start()
+    host_ts = [time.perf_counter()]          # diagnostic only: when the host finished issuing each step
     e0.record()
     for _ in range(args.steps):
         step(leaf, means2D, gc, go)
+        host_ts.append(time.perf_counter())
     e1.record()
     torch.cuda.synchronize()
     sampler.mark_stop()
@@ -303,11 +305,17 @@ def run_ours(args, rank, local_rank, world):
     lib.surfel_profile_read(ms_arr, cnt_arr)
     clocks = sampler.stop() if rank == 0 else None
     t_ms = e0.elapsed_time(e1)
-    tt = torch.tensor([t_ms], device=dev)
+    # per-step host intervals (the host runs at most one R-wait ahead of the device, so in steady state they
+    # track the device step time; isolated long ones are host hiccups): median / p95 / max, worst rank
+    iv = sorted((b - a) * 1e3 for a, b in zip(host_ts[:-1], host_ts[1:]))
+    host_iv = [iv[len(iv) // 2], iv[min(len(iv) - 1, int(0.95 * len(iv)))], iv[-1]] if iv else [0.0, 0.0, 0.0]
+    tt = torch.tensor([t_ms] + host_iv, device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     barrier()
-    t_ms = float(tt.item())
+    t_ms = float(tt[0].item())
+    host_step_ms = {"median": float(tt[1].item()), "p95": float(tt[2].item()), "max": float(tt[3].item()),
+                    "what": "host-side interval between consecutive steps of the timed loop, max over ranks (diagnostic)"}
     ms_per_step = t_ms / args.steps
     value = world * P / (ms_per_step * 1e-3) / 1e6
 
@@ -424,7 +432,7 @@ def run_ours(args, rank, local_rank, world):
                        "host_numa_node": numa_node,
                        "l2_policy": "inputs larger than L2 (232 MB of splat parameters + 83 MB of outputs per step vs 126 MB L2)"},
             "e2e": e2e, "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
-            "roofline": roofline, "clocks": clocks,
+            "roofline": roofline, "clocks": clocks, "host_step_ms": host_step_ms,
         }
         if cpu_baseline is not None:
             out["cpu_baseline"] = cpu_baseline
