@@ -25,9 +25,7 @@ SOURCES = {
     "radix_sort.cu": [],
     "bucket_sort.cu": [],
     "render_fwd.cu": [],
-    "render_fwd_g8.cu": [],
     "render_bwd.cu": [],
-    "render_bwd_tma.cu": [],
     "postprocess.cu": [],
     "loss.cu": [],
     "optim.cu": [],

@@ -25,15 +25,14 @@ namespace {
 
 // Kernel variants (same architecture, alternative implementations kept for A/B measurement).
 // Defaults come from the environment once; surfel_set_variant() changes them at run time (tests).
-struct Variants { int sort_radix, fwd_g8, bwd_tma; };
+struct Variants { int sort_radix; };
 Variants& variants() {
     static Variants v = [] {
         auto is = [](const char* name, const char* val) { const char* e = getenv(name); return e && !strcmp(e, val) ? 1 : 0; };
-        return Variants{is("SURFEL_SORT", "radix"), is("SURFEL_RENDER_FWD", "g8"), is("SURFEL_RENDER_BWD", "tma")};
+        return Variants{is("SURFEL_SORT", "radix")};
     }();
     return v;
 }
-bool use_slab() { return variants().bwd_tma != 0; }
 
 struct Frame { int W, H, gx, gy, row0, row1, tiles; };
 
@@ -68,14 +67,11 @@ BinningLayout binning_layout(size_t R, int tiles) {
     L.vals_b = o;    o = align_up(o + r * 4, 256);
     L.ranges = o;    o = align_up(o + (size_t)tiles * 8, 256);
     L.sort_temp = o; o = align_up(o + std::max(radix_sort_temp_bytes(r), bucket_temp_bytes(tiles)), 256);
-    // optional: per-tile SORTED slab of splat records (R x 96 B) written by the forward's staging and
-    // streamed back by the TMA backward with one bulk copy per stage (SURFEL_RENDER_BWD=tma only)
-    L.slab = o; if (use_slab()) o = align_up(o + r * kRecBytes, 256);
     L.total = o;
     return L;
 }
 
-struct BinView { uint64_t *k_unsorted, *k_sorted; uint32_t *v_unsorted, *v_sorted; uint64_t *k_a, *k_b; uint32_t *v_a, *v_b; uint2* ranges; void* temp; float4* slab; };
+struct BinView { uint64_t *k_unsorted, *k_sorted; uint32_t *v_unsorted, *v_sorted; uint64_t *k_a, *k_b; uint32_t *v_a, *v_b; uint2* ranges; void* temp; };
 
 BinView bin_view(void* ws, size_t R, const Frame& f) {
     BinningLayout L = binning_layout(R, f.tiles);
@@ -88,7 +84,6 @@ BinView bin_view(void* ws, size_t R, const Frame& f) {
     v.k_sorted = in_b ? v.k_b : v.k_a; v.v_sorted = in_b ? v.v_b : v.v_a;
     v.ranges = (uint2*)(c + L.ranges);
     v.temp = c + L.sort_temp;
-    v.slab = use_slab() ? (float4*)(c + L.slab) : nullptr;
     return v;
 }
 
@@ -115,10 +110,6 @@ int surfel_set_variant(const char* name, const char* value) {
     Variants& v = variants();
     if (!strcmp(name, "sort")) {
         if (!strcmp(value, "bucket")) v.sort_radix = 0; else if (!strcmp(value, "radix")) v.sort_radix = 1; else goto bad;
-    } else if (!strcmp(name, "render_fwd")) {
-        if (!strcmp(value, "warp")) v.fwd_g8 = 0; else if (!strcmp(value, "g8")) v.fwd_g8 = 1; else goto bad;
-    } else if (!strcmp(name, "render_bwd")) {
-        if (!strcmp(value, "classic")) v.bwd_tma = 0; else if (!strcmp(value, "tma")) v.bwd_tma = 1; else goto bad;
     } else goto bad;
     return 0;
 bad:
@@ -141,6 +132,7 @@ size_t surfel_binning_bytes(size_t R, int W, int H) {
 int surfel_geom_offsets(int P, size_t* out) {
     GeomLayout L = geom_layout(P);
     out[0] = L.rec; out[1] = L.tiles_touched; out[2] = L.offsets; out[3] = L.clamped; out[4] = L.counters;
+    out[5] = L.tmat;
     return 0;
 }
 int surfel_binning_offsets(size_t R, int W, int H, size_t* out) {
@@ -186,7 +178,7 @@ int surfel_forward_preprocess(const surfel_settings_t* s, int P, int M, const fl
     p.means3D = means3D; p.scales = scales; p.rotations = rotations; p.opacities = opacities;
     p.shs = shs; p.transMat_precomp = transMat_precomp; p.colors_precomp = colors_precomp;
     p.viewmatrix = s->viewmatrix; p.projmatrix = s->projmatrix; p.campos = s->campos;
-    p.radii = radii; p.rec = (float4*)(g + L.rec); p.tiles_touched = (uint32_t*)(g + L.tiles_touched);
+    p.radii = radii; p.rec = (float4*)(g + L.rec); p.tmat = (float4*)(g + L.tmat); p.tiles_touched = (uint32_t*)(g + L.tiles_touched);
     p.offsets = (uint32_t*)(g + L.offsets); p.clamped = (uint8_t*)(g + L.clamped);
     p.scan_status = (unsigned long long*)(g + L.scan_status); p.counters = (uint32_t*)(g + L.counters);
     p.tile_count = image_ws ? (uint32_t*)((char*)image_ws + image_layout(f.W, f.H).tile_count) : nullptr;
@@ -205,7 +197,7 @@ int surfel_bin_duplicate(const surfel_settings_t* s, int P, uint32_t R, const vo
     GeomLayout L = geom_layout(P);
     const char* g = (const char*)geom_ws;
     BinView v = bin_view(binning_ws, R, f);
-    return launch_duplicate_with_keys(P, f.gx, f.gy, f.row0, f.row1, (const float4*)(g + L.rec), radii,
+    return launch_duplicate_with_keys(P, f.gx, f.gy, f.row0, f.row1, (const float4*)(g + L.tmat), radii,
                                       (const uint32_t*)(g + L.offsets), v.k_unsorted, v.v_unsorted,
                                       (cudaStream_t)stream);
 }
@@ -234,12 +226,7 @@ int surfel_render_forward(const surfel_settings_t* s, uint32_t R, const void* ge
     p.bg = s->bg;
     p.out_color = out_color; p.out_others = out_others;
     p.accum = (float*)((char*)image_ws + I.accum); p.n_contrib = (uint32_t*)((char*)image_ws + I.n_contrib);
-    p.slab = v.slab;
-    // SURFEL_RENDER_FWD=g8 selects the experimental mapping "four 8-lane groups per warp, one splat
-    // per group" (render_fwd_g8.cu): 1.5x fewer blend rounds but measured SLOWER on B200 (0.487 ms vs
-    // 0.452 ms at the headline workload; 4 distinct smem addresses per load, no warp-uniform skips).
-    const bool use_g8 = variants().fwd_g8 != 0;
-    return use_g8 ? launch_render_fwd_g8(p, (cudaStream_t)stream) : launch_render_fwd(p, (cudaStream_t)stream);
+    return launch_render_fwd(p, (cudaStream_t)stream);
 }
 
 int surfel_bin_bucket(const surfel_settings_t* s, int P, uint32_t R, const void* geom_ws,
@@ -252,7 +239,7 @@ int surfel_bin_bucket(const surfel_settings_t* s, int P, uint32_t R, const void*
     BinView v = bin_view(binning_ws, R, f);
     // scratch pairs live in whichever key buffer does NOT receive the sorted keys
     unsigned long long* pairs = (unsigned long long*)(v.k_sorted == v.k_a ? v.k_b : v.k_a);
-    return launch_bucket_binning(P, R, f.gx, f.gy, f.row0, f.row1, (const float4*)(g + L.rec), radii,
+    return launch_bucket_binning(P, R, f.gx, f.gy, f.row0, f.row1, (const float4*)(g + L.tmat), radii,
                                  (const uint32_t*)(g + L.offsets), pairs, v.v_sorted,
                                  write_keys ? (unsigned long long*)v.k_sorted : nullptr, v.ranges, v.temp,
                                  image_ws_with_counts ? (const uint32_t*)((const char*)image_ws_with_counts +
@@ -299,10 +286,8 @@ int surfel_backward(const surfel_settings_t* s, int P, int M, uint32_t R, const 
         p.ranges = v.ranges; p.point_list = v.v_sorted; p.rec = (const float4*)(g + L.rec); p.bg = s->bg;
         p.accum = (float*)((char*)image_ws + I.accum); p.n_contrib = (uint32_t*)((char*)image_ws + I.n_contrib);
         p.dL_dpix = dL_dout_color; p.dL_dothers = dL_dout_others; p.grad_rec = grad_scratch;
-        p.slab = v.slab;
         p.lowpass_quirk = lowpass_depth_quirk;
-        const bool use_tma = variants().bwd_tma != 0 && v.slab != nullptr;
-        if (use_tma ? launch_render_bwd_tma(p, st) : launch_render_bwd(p, st)) return 1;
+        if (launch_render_bwd(p, st)) return 1;
     }
     PreBwdParams q;
     memset(&q, 0, sizeof(q));
@@ -310,7 +295,7 @@ int surfel_backward(const surfel_settings_t* s, int P, int M, uint32_t R, const 
     q.means3D = means3D; q.scales = scales; q.rotations = rotations; q.shs = shs;
     q.transMat_precomp = transMat_precomp; q.has_colors_precomp = has_colors_precomp;
     q.viewmatrix = s->viewmatrix; q.projmatrix = s->projmatrix; q.campos = s->campos;
-    q.radii = radii; q.rec = (const float4*)(g + L.rec); q.clamped = (const uint8_t*)(g + L.clamped);
+    q.radii = radii; q.tmat = (const float4*)(g + L.tmat); q.clamped = (const uint8_t*)(g + L.clamped);
     q.grad_rec = grad_scratch;
     q.dL_dmeans2D = dL_dmeans2D; q.dL_dcolors = dL_dcolors; q.dL_dopacity = dL_dopacity;
     q.dL_dmeans3D = dL_dmeans3D; q.dL_dtransMat = dL_dtransMat; q.dL_dsh = dL_dsh;

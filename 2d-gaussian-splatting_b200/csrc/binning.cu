@@ -18,7 +18,7 @@ namespace surfel {
 constexpr int kDupBlock = 256;
 
 __global__ void __launch_bounds__(kDupBlock)
-duplicate_with_keys_kernel(int P, int gx, int gy, int row0, int row1, const float4* __restrict__ rec,
+duplicate_with_keys_kernel(int P, int gx, int gy, int row0, int row1, const float4* __restrict__ tmat,
                            const int* __restrict__ radii, const uint32_t* __restrict__ offsets,
                            uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     __shared__ uint32_t s_end[kDupBlock];
@@ -35,12 +35,11 @@ duplicate_with_keys_kernel(int P, int gx, int gy, int row0, int row1, const floa
     if (idx < P) {
         const int r = radii[idx];
         if (r > 0) {
-            const float4 q2 = rec[(size_t)idx * kRecQuads + 2];
-            const float4 q3 = rec[(size_t)idx * kRecQuads + 3];
+            const float4 t2 = tmat[(size_t)idx * kTmQuads + 2];      // (Tw.z, xy.x, xy.y, view depth)
             int x1, y1;
-            get_rect(q2.y, q2.z, r, gx, gy, row0, row1, x0, y0, x1, y1);
+            get_rect(t2.y, t2.z, r, gx, gy, row0, row1, x0, y0, x1, y1);
             w = max(1, x1 - x0);
-            dbits = __float_as_uint(q3.w);
+            dbits = __float_as_uint(t2.w);
         }
     }
     s_x0[tid] = x0; s_y0[tid] = y0; s_w[tid] = w; s_depth[tid] = dbits;
@@ -76,13 +75,13 @@ __global__ void identify_tile_ranges_kernel(size_t R, const uint64_t* __restrict
     if (i == R - 1) ranges[tile].y = (uint32_t)R;
 }
 
-int launch_duplicate_with_keys(int P, int gx, int gy, int row0, int row1, const float4* rec,
+int launch_duplicate_with_keys(int P, int gx, int gy, int row0, int row1, const float4* tmat,
                                const int* radii, const uint32_t* offsets, uint64_t* keys,
                                uint32_t* vals, cudaStream_t stream) {
     if (P <= 0) return 0;
     LaunchScope scope(kStDuplicate, stream);
     duplicate_with_keys_kernel<<<(P + kDupBlock - 1) / kDupBlock, kDupBlock, 0, stream>>>(
-        P, gx, gy, row0, row1, rec, radii, offsets, keys, vals);
+        P, gx, gy, row0, row1, tmat, radii, offsets, keys, vals);
     SURFEL_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -32,7 +32,7 @@ constexpr int kLargeMax = 16384;         // entries sorted in 128 KB of dynamic 
 // Shared helper: block of 256 splats -> flattened instance walk.  F(tile, depth_bits, splat_idx).
 template <typename F>
 __device__ __forceinline__ void walk_instances(int P, int gx, int gy, int row0, int row1,
-                                               const float4* __restrict__ rec, const int* __restrict__ radii,
+                                               const float4* __restrict__ tmat, const int* __restrict__ radii,
                                                const uint32_t* __restrict__ offsets, F f) {
     __shared__ uint32_t s_end[kWalkBlock];
     __shared__ int s_x0[kWalkBlock], s_y0[kWalkBlock], s_w[kWalkBlock];
@@ -48,12 +48,11 @@ __device__ __forceinline__ void walk_instances(int P, int gx, int gy, int row0, 
     if (idx < P) {
         const int r = radii[idx];
         if (r > 0) {
-            const float4 q2 = rec[(size_t)idx * kRecQuads + 2];
-            const float4 q3 = rec[(size_t)idx * kRecQuads + 3];
+            const float4 t2 = tmat[(size_t)idx * kTmQuads + 2];      // (Tw.z, xy.x, xy.y, view depth)
             int x1, y1;
-            get_rect(q2.y, q2.z, r, gx, gy, row0, row1, x0, y0, x1, y1);
+            get_rect(t2.y, t2.z, r, gx, gy, row0, row1, x0, y0, x1, y1);
             w = max(1, x1 - x0);
-            dbits = __float_as_uint(q3.w);
+            dbits = __float_as_uint(t2.w);
         }
     }
     s_x0[tid] = x0; s_y0[tid] = y0; s_w[tid] = w; s_depth[tid] = dbits;
@@ -76,10 +75,10 @@ __device__ __forceinline__ void walk_instances(int P, int gx, int gy, int row0, 
 }
 
 __global__ void __launch_bounds__(kWalkBlock)
-tile_count_kernel(int P, int gx, int gy, int row0, int row1, const float4* __restrict__ rec,
+tile_count_kernel(int P, int gx, int gy, int row0, int row1, const float4* __restrict__ tmat,
                   const int* __restrict__ radii, const uint32_t* __restrict__ offsets,
                   uint32_t* __restrict__ tile_count) {
-    walk_instances(P, gx, gy, row0, row1, rec, radii, offsets,
+    walk_instances(P, gx, gy, row0, row1, tmat, radii, offsets,
                    [&](uint32_t tile, uint32_t, uint32_t) { atomicAdd(tile_count + tile, 1u); });
 }
 
@@ -126,10 +125,10 @@ tile_scan_kernel(int tiles, uint32_t cap, const uint32_t* __restrict__ tile_coun
 }
 
 __global__ void __launch_bounds__(kWalkBlock)
-tile_scatter_kernel(int P, int gx, int gy, int row0, int row1, const float4* __restrict__ rec,
+tile_scatter_kernel(int P, int gx, int gy, int row0, int row1, const float4* __restrict__ tmat,
                     const int* __restrict__ radii, const uint32_t* __restrict__ offsets,
                     uint32_t* __restrict__ tile_fill, unsigned long long* __restrict__ pairs, uint32_t cap) {
-    walk_instances(P, gx, gy, row0, row1, rec, radii, offsets,
+    walk_instances(P, gx, gy, row0, row1, tmat, radii, offsets,
                    [&](uint32_t tile, uint32_t dbits, uint32_t idx) {
                        const uint32_t slot = atomicAdd(tile_fill + tile, 1u);
                        if (slot < cap) pairs[slot] = ((unsigned long long)dbits << 32) | idx;
@@ -406,7 +405,7 @@ tile_sort_large_kernel(const uint2* __restrict__ ranges, unsigned long long* __r
 
 size_t bucket_temp_bytes(int tiles) { return align_up((size_t)tiles * 4, 256) * 4 + 512; }
 
-int launch_bucket_binning(int P, size_t R, int gx, int gy, int row0, int row1, const float4* rec,
+int launch_bucket_binning(int P, size_t R, int gx, int gy, int row0, int row1, const float4* tmat,
                           const int* radii, const uint32_t* offsets, unsigned long long* pairs,
                           uint32_t* point_list, unsigned long long* keys_sorted, uint2* ranges,
                           void* temp, const uint32_t* tile_count_ready, cudaStream_t stream) {
@@ -427,7 +426,7 @@ int launch_bucket_binning(int P, size_t R, int gx, int gy, int row0, int row1, c
     }
     if (!tile_count_ready && P > 0 && R > 0) {
         LaunchScope scope(kStTileCount, stream);
-        tile_count_kernel<<<blocks, kWalkBlock, 0, stream>>>(P, gx, gy, row0, row1, rec, radii, offsets, tile_count);
+        tile_count_kernel<<<blocks, kWalkBlock, 0, stream>>>(P, gx, gy, row0, row1, tmat, radii, offsets, tile_count);
         SURFEL_CUDA_OK(cudaGetLastError());
     }
     {
@@ -438,7 +437,7 @@ int launch_bucket_binning(int P, size_t R, int gx, int gy, int row0, int row1, c
     if (P <= 0 || R == 0) return 0;
     {
         LaunchScope scope(kStTileScatter, stream);
-        tile_scatter_kernel<<<blocks, kWalkBlock, 0, stream>>>(P, gx, gy, row0, row1, rec, radii, offsets, tile_fill, pairs, (uint32_t)std::min<size_t>(R, 0xffffffffu));
+        tile_scatter_kernel<<<blocks, kWalkBlock, 0, stream>>>(P, gx, gy, row0, row1, tmat, radii, offsets, tile_fill, pairs, (uint32_t)std::min<size_t>(R, 0xffffffffu));
         SURFEL_CUDA_OK(cudaGetLastError());
     }
     {

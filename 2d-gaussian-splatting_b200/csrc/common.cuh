@@ -26,35 +26,60 @@ constexpr int kChDepth = 0, kChAlpha = 1, kChNormal = 2, kChMidDepth = 5, kChDis
 
 // ---------------------------------------------------------------------------------------------
 // HBM layout of the per-splat state written by preprocess and gathered by render (fwd and bwd).
-// One 96-byte record = 3 full 32-byte sectors, 16-byte aligned, read with 128-bit loads:
-//   q0 = (Tu.x, Tu.y, Tu.z, Tv.x)      q1 = (Tv.y, Tv.z, Tw.x, Tw.y)
-//   q2 = (Tw.z, xy.x, xy.y, opacity)   q3 = (n.x, n.y, n.z, depth)
-//   q4 = (r, g, b, unused)             q5 = conservative screen bbox (x0, y0, x1, y1) of the
-//                                           region where alpha can reach 1/255 (render culling)
+//
+// RENDER RECORD: 128 bytes = one full cache line, read with 128-bit loads.  The ray-splat
+// intersection of upstream's renderCUDA (k = px*Tw - Tu, l = py*Tw - Tv, p = cross(k, l))
+// is AFFINE in the pixel:  p(px,py) = Tu x Tv + px (Tv x Tw) + py (Tw x Tu)  — the adjugate of the
+// splat->pixel homography applied to (px, py, 1).  Preprocess therefore emits the three vectors once
+// per splat, expanded about the splat's own screen position c = xy (the AABB centre of A.1 step 5):
+//      p = Pc + (px - c.x) P1 + (py - c.y) P2,   P1 = Tv' x Tw,  P2 = Tw x Tu',  Pc = Tu' x Tv',
+//      Tu' = Tu - c.x Tw,  Tv' = Tv - c.y Tw
+// computed in double and rounded once (in absolute pixel coordinates the float32 terms cancel to a few
+// units in 1e5).  The render kernels spend 6 FMA per (pixel, splat) on p instead of 6 FMA + 3 MUL +
+// 3 FMA for k, l and their cross product, and the result is closer to the exact value of upstream's
+// formula than upstream's own float32 evaluation.  The ray-splat depth s.x*Tw.x + s.y*Tw.y + Tw.z equals
+// det(T) / p.z exactly (w of the intersection point), which is how the forward evaluates it.
+//   q0 = (P1.x, P1.y, P1.z, c.x)        q1 = (P2.x, P2.y, P2.z, c.y)
+//   q2 = (Pc.x, Pc.y, Pc.z, opacity)    q3 = (n.x, n.y, n.z, Tw.z)          n = view-space normal
+//   q4 = (r, g, b, det T)               q5 = (Tw.x, Tw.y, splat index bits, view depth)
+//   q6 = conservative screen AABB (x0, y0, x1, y1) of the region where alpha can reach 1/255
+//   q7 = extents of the same region along the diagonals (min x+y, max x+y, min x-y, max x-y)
+// q6/q7 are only read while a tile's list is staged (each staging thread classifies its splat against
+// the eight 8x4 warp footprints of the tile); q0..q5 (q0..q4 in the forward) go to shared memory.
 // ---------------------------------------------------------------------------------------------
-constexpr int kRecQuads = 6;
+constexpr int kRecQuads = 8;
 constexpr int kRecBytes = kRecQuads * 16;
+constexpr int kRecQuadsFwd = 5;     // quads the forward stages in shared memory
+constexpr int kRecQuadsBwd = 6;     // quads the backward stages
+
+// TRANSFORM RECORD: 48 bytes per splat, upstream's geometry-state fields that the render kernels do
+// not need but preprocess backward, the binning kernels and the parity tests do:
+//   t0 = (Tu.x, Tu.y, Tu.z, Tv.x)   t1 = (Tv.y, Tv.z, Tw.x, Tw.y)   t2 = (Tw.z, xy.x, xy.y, view depth)
+constexpr int kTmQuads = 3;
 
 // Per-splat gradient record accumulated by render backward (float atomics), 24 floats = 96 B.
-// dL_dtransMat is NOT accumulated directly: with dp = dL/d(cross(k,l)) per (pixel,splat) and
-// (dx,dy) = pixel - AABB centre, the sums  A = sum dp,  Bx = sum dx*dp,  By = sum dy*dp,
-// Z = sum dL_dz*(s.x, s.y, 1)  determine it exactly (the px*py terms cancel):
-//   dTu = -(lc x A) - (Tw x By),  dTv = -(A x kc) - (Bx x Tw),
-//   dTw = -cx*dTu - cy*dTv + lc x Bx + By x kc + Z,   kc = cx*Tw - Tu, lc = cy*Tw - Tv
-// which preprocess backward evaluates once per splat instead of every lane doing two cross products.
-//   [0..2] A  [3..5] Bx  [6..8] By  [9..11] Z  [12..13] dL_dmean2D.xy  [14] dL_dopacity
-//   [15..17] dL_dnormal  [18..20] dL_dcolor  [21..23] pad
+// dL_dtransMat is NOT accumulated directly.  With a = dL/dp per (pixel,splat) (p = Pc + dx P1 + dy P2, the
+// affine form above, (dx,dy) = pixel - c) the sums  A = sum a,  Bx = sum dx*a,  By = sum dy*a  ARE the
+// gradients of (Pc, P1, P2); the ray-splat depth det T / p.z contributes -dL_dz*depth/p.z to a.z and
+// Zd = sum dL_dz / p.z  (the gradient of det T); the low-pass branch contributes Zl = sum dL_dz*(s.x, s.y, 1)
+// to dL_dTw (upstream's "Propagate the gradients of depth"; (0, 0, dL_dz) with the exact derivative).
+// Preprocess backward turns them into dL_dT once per splat (three cross products + det's gradient) instead
+// of every lane doing two cross products per pair:
+//   dTu' = Tv' x A + By x Tw,  dTv' = A x Tu' + Tw x Bx,  dTw = Bx x Tv' + Tu' x By - c.x dTu' - c.y dTv'
+//   (+ Zd * (Tv x Tw, Tw x Tu, Tu x Tv) + Zl on Tw)
+//   [0..2] A  [3..5] Bx  [6..8] By  [9] Zd  [10..12] Zl  [13..14] dL_dmean2D.xy  [15] dL_dopacity
+//   [16..18] dL_dnormal  [19..21] dL_dcolor  [22..23] pad
 constexpr int kGradFloats = 24;
-constexpr int kGradUsed = 21;
+constexpr int kGradUsed = 22;
 
 struct GeomLayout {
-    size_t rec, tiles_touched, offsets, clamped, scan_status, counters, total;
+    size_t rec, tmat, tiles_touched, offsets, clamped, scan_status, counters, total;
 };
 struct ImageLayout {
     size_t accum, n_contrib, tile_count, total;  // accum: final_T, M1, M2; n_contrib: last, median; per-tile instance counts
 };
 struct BinningLayout {
-    size_t keys_a, keys_b, vals_a, vals_b, ranges, sort_temp, slab, total;
+    size_t keys_a, keys_b, vals_a, vals_b, ranges, sort_temp, total;
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -66,6 +91,7 @@ inline GeomLayout geom_layout(int P) {
     size_t o = 0;
     size_t p = (size_t)(P > 0 ? P : 1);
     L.rec = o;            o = align_up(o + p * kRecBytes, 256);
+    L.tmat = o;           o = align_up(o + p * kTmQuads * 16, 256);
     L.tiles_touched = o;  o = align_up(o + p * 4, 256);
     L.offsets = o;        o = align_up(o + p * 4, 256);
     L.clamped = o;        o = align_up(o + p, 256);

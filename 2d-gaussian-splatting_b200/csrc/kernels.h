@@ -12,7 +12,7 @@ struct PreFwdParams {
     const float* means3D; const float* scales; const float* rotations; const float* opacities;
     const float* shs; const float* transMat_precomp; const float* colors_precomp;
     const float* viewmatrix; const float* projmatrix; const float* campos;
-    int* radii; float4* rec; uint32_t* tiles_touched; uint32_t* offsets; uint8_t* clamped;
+    int* radii; float4* rec; float4* tmat; uint32_t* tiles_touched; uint32_t* offsets; uint8_t* clamped;
     unsigned long long* scan_status; uint32_t* counters;
     uint32_t* tile_count;   // optional (tiles): per-tile instance counts accumulated here (fused count)
     uint32_t* num_rendered_mapped;   // optional: device-visible alias of the caller's pinned host word for R
@@ -24,7 +24,7 @@ struct PreBwdParams {
     const float* means3D; const float* scales; const float* rotations; const float* shs;
     const float* transMat_precomp; int has_colors_precomp;
     const float* viewmatrix; const float* projmatrix; const float* campos;
-    const int* radii; const float4* rec; const uint8_t* clamped;
+    const int* radii; const float4* tmat; const uint8_t* clamped;
     const float* grad_rec;            // (P, kGradFloats) accumulated by render backward
     float* dL_dmeans2D;               // (P,3) out: densification proxy in .xy
     float* dL_dcolors;                // (P,3) out (gradient of colors_precomp)
@@ -44,7 +44,6 @@ struct RenderParams {
     float* out_color; float* out_others; float* accum; uint32_t* n_contrib;
     // backward
     const float* dL_dpix; const float* dL_dothers; float* grad_rec; int lowpass_quirk;
-    float4* slab;   // optional (R x 6 quads): records in sorted tile-list order (forward writes, TMA backward reads)
 };
 
 int launch_preprocess_fwd(const PreFwdParams& p, cudaStream_t stream);
@@ -53,7 +52,7 @@ int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, ui
 int launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t stream);
 
 // binning
-int launch_duplicate_with_keys(int P, int gx, int gy, int row0, int row1, const float4* rec,
+int launch_duplicate_with_keys(int P, int gx, int gy, int row0, int row1, const float4* tmat,
                                const int* radii, const uint32_t* offsets, uint64_t* keys,
                                uint32_t* vals, cudaStream_t stream);
 int launch_identify_tile_ranges(size_t R, int tiles, const uint64_t* keys_sorted, uint2* ranges,
@@ -72,14 +71,12 @@ int launch_radix_sort_pairs(uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b
 // Produces ranges + point_list (+ keys_sorted if non-NULL) identical to duplicate -> stable radix
 // sort -> identifyTileRanges.  `pairs` is an R x u64 scratch buffer.
 size_t bucket_temp_bytes(int tiles);
-int launch_bucket_binning(int P, size_t R, int gx, int gy, int row0, int row1, const float4* rec,
+int launch_bucket_binning(int P, size_t R, int gx, int gy, int row0, int row1, const float4* tmat,
                           const int* radii, const uint32_t* offsets, unsigned long long* pairs,
                           uint32_t* point_list, unsigned long long* keys_sorted, uint2* ranges,
                           void* temp, const uint32_t* tile_count_ready, cudaStream_t stream);
 
 int launch_render_fwd(const RenderParams& p, cudaStream_t stream);
 int launch_render_bwd(const RenderParams& p, cudaStream_t stream);
-int launch_render_bwd_tma(const RenderParams& p, cudaStream_t stream);  // TMA bulk copy + mbarrier pipeline
-int launch_render_fwd_g8(const RenderParams& p, cudaStream_t stream);   // 4 groups of 8 lanes per warp
 
 }  // namespace surfel

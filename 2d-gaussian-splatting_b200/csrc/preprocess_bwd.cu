@@ -5,7 +5,8 @@
 //   1. fold dL_dmean2D (low-pass branch) into dL_dT through the AABB-centre formula,
 //   2. dL_dT -> dL_dmean3D, dL_dscale, dL_dq (unit quaternion) and the normal's vjp,
 //   3. SH backward (dL_dsh, and dL_dmean3D through the view direction),
-//   4. overwrite dL_dmean2D with the densification proxy dL_dT[2|5] * depth * 0.5 * (W|H).
+//   4. overwrite dL_dmean2D with the densification proxy dL_dT[2|5] * depth * 0.5 * (W|H)
+//      (dL_dT before step 1 on the scales+rotations path, after it on the transMat_precomp path, as upstream).
 // The kernel writes EVERY output row (zeros for culled splats), so the caller can hand in
 // uninitialised tensors: no separate zero-fill pass over the 59 floats/splat of gradients.
 // Kept quirk: dL_dscale ignores scale_modifier (only the viewer uses modifier != 1).
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(128, 6) preprocess_bwd_kernel(PreBwdParams p) 
     float gm2x = 0, gm2y = 0, gopa = 0, gn[3] = {0, 0, 0}, gc[3] = {0, 0, 0};
     float tm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     float g3[3] = {0, 0, 0}, gs[2] = {0, 0}, gq[4] = {0, 0, 0, 0};
-    float px = 0, py = 0, pz = 0;
+    float px = 0, py = 0, pz = 0, proxy2 = 0, proxy5 = 0;
 
     // Every input of the splat is requested in the first round trip to HBM: the SH rows by cp.async
     // (LDGSTS) straight into the warp's panel, position / rotation / scale into registers, while the
@@ -79,34 +80,44 @@ __global__ void __launch_bounds__(128, 6) preprocess_bwd_kernel(PreBwdParams p) 
     if (visible) {
         const float4* gr = reinterpret_cast<const float4*>(p.grad_rec + (size_t)idx * kGradFloats);
         const float4 a = gr[0], b = gr[1], c = gr[2], d = gr[3], e = gr[4], f5 = gr[5];
-        const float4* r = p.rec + (size_t)idx * kRecQuads;
+        const float4* r = p.tmat + (size_t)idx * kTmQuads;      // (Tu, Tv.x) (Tv.yz, Tw.xy) (Tw.z, xy, depth)
         const float4 q0 = r[0], q1 = r[1], q2 = r[2];
         tm[0] = q0.x; tm[1] = q0.y; tm[2] = q0.z; tm[3] = q0.w; tm[4] = q1.x; tm[5] = q1.y;
         tm[6] = q1.z; tm[7] = q1.w; tm[8] = q2.x;
-        gm2x = d.x; gm2y = d.y; gopa = d.z;
-        gn[0] = d.w; gn[1] = e.x; gn[2] = e.y; gc[0] = e.z; gc[1] = e.w; gc[2] = f5.x;
+        gm2x = d.y; gm2y = d.z; gopa = d.w;
+        gn[0] = e.x; gn[1] = e.y; gn[2] = e.z; gc[0] = e.w; gc[1] = f5.x; gc[2] = f5.y;
         {
-            // dL_dT from the accumulated sums A, Bx, By, Z (record layout: common.cuh)
-            const float A[3] = {a.x, a.y, a.z}, Bx[3] = {a.w, b.x, b.y}, By[3] = {b.z, b.w, c.x}, Z[3] = {c.y, c.z, c.w};
+            // dL_dT from the accumulated sums A, Bx, By, Zd, Zl (record layout: common.cuh)
+            const float A[3] = {a.x, a.y, a.z}, Bx[3] = {a.w, b.x, b.y}, By[3] = {b.z, b.w, c.x};
+            const float Zd = c.y, Zl[3] = {c.z, c.w, d.x};
             const float cx = q2.y, cy = q2.z;
-            const float kc[3] = {cx * tm[6] - tm[0], cx * tm[7] - tm[1], cx * tm[8] - tm[2]};
-            const float lc[3] = {cy * tm[6] - tm[3], cy * tm[7] - tm[4], cy * tm[8] - tm[5]};
-            const float* Tw = tm + 6;
+            // -Tu' = cx Tw - Tu and -Tv' in double: cx*Tw.z and Tu.z agree to a few units in 1e5
+            const float kc[3] = {(float)((double)cx * tm[6] - (double)tm[0]), (float)((double)cx * tm[7] - (double)tm[1]), (float)((double)cx * tm[8] - (double)tm[2])};
+            const float lc[3] = {(float)((double)cy * tm[6] - (double)tm[3]), (float)((double)cy * tm[7] - (double)tm[4]), (float)((double)cy * tm[8] - (double)tm[5])};
+            const float* Tu = tm; const float* Tv = tm + 3; const float* Tw = tm + 6;
 #define CROSS(o, u, v) do { o[0] = u[1] * v[2] - u[2] * v[1]; o[1] = u[2] * v[0] - u[0] * v[2]; o[2] = u[0] * v[1] - u[1] * v[0]; } while (0)
             float t1[3], t2[3], t3[3], t4[3];
-            CROSS(t1, lc, A); CROSS(t2, Tw, By);          // dTu = -(lc x A) - (Tw x By)
-            CROSS(t3, A, kc); CROSS(t4, Bx, Tw);          // dTv = -(A x kc) - (Bx x Tw)
+            CROSS(t1, lc, A); CROSS(t2, Tw, By);          // dTu' = -(lc x A) - (Tw x By) = Tv' x A + By x Tw
+            CROSS(t3, A, kc); CROSS(t4, Bx, Tw);          // dTv' = -(A x kc) - (Bx x Tw) = A x Tu' + Tw x Bx
             float u1[3], u2[3];
-            CROSS(u1, lc, Bx); CROSS(u2, By, kc);
+            CROSS(u1, lc, Bx); CROSS(u2, By, kc);         // Bx x Tv' + Tu' x By
+            float d1[3], d2[3], d3[3];                    // gradient of det T: (Tv x Tw, Tw x Tu, Tu x Tv)
+            CROSS(d1, Tv, Tw); CROSS(d2, Tw, Tu); CROSS(d3, Tu, Tv);
 #undef CROSS
 #pragma unroll
             for (int k = 0; k < 3; k++) {
-                gT[k] = -t1[k] - t2[k];
-                gT[3 + k] = -t3[k] - t4[k];
-                gT[6 + k] = -cx * gT[k] - cy * gT[3 + k] + u1[k] + u2[k] + Z[k];
+                const float gu = -t1[k] - t2[k], gv = -t3[k] - t4[k];
+                gT[k] = gu + Zd * d1[k];
+                gT[3 + k] = gv + Zd * d2[k];
+                gT[6 + k] = -cx * gu - cy * gv + u1[k] + u2[k] + Zd * d3[k] + Zl[k];
             }
         }
 
+        // Densification proxy source (step 4).  Upstream folds dL_dmean2D into a LOCAL copy of dL_dT and
+        // writes it back only on the transMat_precomp path, so on the scales+rotations (training) path the
+        // proxy reads the RAW render-backward dL_dtransMat[2|5] — without the low-pass filter's gradient
+        // (/root/reference/README.md:118); on the precomp path it reads the folded one.
+        proxy2 = gT[2]; proxy5 = gT[5];
         // 1. AABB-centre vjp
         if (gm2x != 0.0f || gm2y != 0.0f) {
             const float t[3] = {kCutoff * kCutoff, kCutoff * kCutoff, -1.0f};
@@ -124,6 +135,7 @@ __global__ void __launch_bounds__(128, 6) preprocess_bwd_kernel(PreBwdParams p) 
 #pragma unroll
             for (int k = 0; k < 3; k++) gT[6 + k] += dT3[k] + dL_dd * (t[k] * tm[6 + k] * 2.0f);
         }
+        if (!geom) { proxy2 = gT[2]; proxy5 = gT[5]; }
 
         if (geom) {
             const float* vm = p.viewmatrix;
@@ -274,8 +286,8 @@ __global__ void __launch_bounds__(128, 6) preprocess_bwd_kernel(PreBwdParams p) 
     // 4. outputs (every row written)
     float* o;
     o = p.dL_dmeans2D + 3 * (size_t)idx;
-    o[0] = visible ? gT[2] * tm[8] * 0.5f * (float)p.W : 0.0f;
-    o[1] = visible ? gT[5] * tm[8] * 0.5f * (float)p.H : 0.0f;
+    o[0] = visible ? proxy2 * tm[8] * 0.5f * (float)p.W : 0.0f;
+    o[1] = visible ? proxy5 * tm[8] * 0.5f * (float)p.H : 0.0f;
     o[2] = 0.0f;
     p.dL_dopacity[idx] = gopa;
     o = p.dL_dmeans3D + 3 * (size_t)idx; o[0] = g3[0]; o[1] = g3[1]; o[2] = g3[2];

@@ -327,47 +327,71 @@ __global__ void __launch_bounds__(kPreBlock, 8) preprocess_fwd_kernel(PreFwdPara
         p.tiles_touched[idx] = tt;
         p.clamped[idx] = (uint8_t)clamp_bits;
         if (visible) {
-            // conservative screen bbox of {alpha >= 1/255}: low-pass disk around xy, united with the
-            // projected ellipse rho3d <= tau when it is bounded (render culling).
-            float bx0, by0, bx1, by1;
+            // ---- render record (common.cuh).  Everything below is evaluated about the splat's own
+            // screen position c = (cx, cy), in double: in absolute pixel coordinates the adjugate and
+            // the conic extents subtract float32 terms of order |pixel|^2 (at 4K the loss
+            // exceeded the culling margin). ----
+            const double Twx = tm[6], Twy = tm[7], Twz = tm[8];
+            const double Tux = (double)tm[0] - (double)cx * Twx, Tuy = (double)tm[1] - (double)cx * Twy, Tuz = (double)tm[2] - (double)cx * Twz;
+            const double Tvx = (double)tm[3] - (double)cy * Twx, Tvy = (double)tm[4] - (double)cy * Twy, Tvz = (double)tm[5] - (double)cy * Twz;
+            // P1 = Tv' x Tw, P2 = Tw x Tu', Pc = Tu' x Tv'
+            const double P1x = Tvy * Twz - Tvz * Twy, P1y = Tvz * Twx - Tvx * Twz, P1z = Tvx * Twy - Tvy * Twx;
+            const double P2x = Twy * Tuz - Twz * Tuy, P2y = Twz * Tux - Twx * Tuz, P2z = Twx * Tuy - Twy * Tux;
+            const double Pcx = Tuy * Tvz - Tuz * Tvy, Pcy = Tuz * Tvx - Tux * Tvz, Pcz = Tux * Tvy - Tuy * Tvx;
+            const double det = Tux * P1x + Tuy * P1y + Tuz * P1z;      // det T (invariant under the shift)
+
+            // conservative region of {alpha >= 1/255} = low-pass disk  U  projected ellipse rho3d <= tau,
+            // as extents along x, y, x+y and x-y relative to c (render culling)
+            float ext[8];     // lo/hi along x, y, u = x+y, v = x-y
             const float a255 = 255.0f * opa;
             if (a255 < 0.999f) {
-                bx0 = by0 = 3.0e38f; bx1 = by1 = -3.0e38f;     // can never reach 1/255: empty box
+#pragma unroll
+                for (int k = 0; k < 4; k++) { ext[2 * k] = 3.0e38f; ext[2 * k + 1] = -3.0e38f; }   // can never reach 1/255: empty
             } else {
                 const float tau = 2.0f * logf(a255) + 0.01f;
                 const float r2 = sqrtf(0.5f * tau) + 0.05f;
-                bx0 = cx - r2; bx1 = cx + r2; by0 = cy - r2; by1 = cy + r2;
-                const float wxy = tm[6] * tm[6] + tm[7] * tm[7];
-                const float wz2 = tm[8] * tm[8];
-                if (tm[8] > 0.0f && wz2 > 1.05f * tau * wxy) {
-                    const float d = tau * wxy - wz2;
-                    const float f0 = tau / d, f2 = -1.0f / d;
-                    const float ecx = f0 * (tm[0] * tm[6] + tm[1] * tm[7]) + f2 * (tm[2] * tm[8]);
-                    const float ecy = f0 * (tm[3] * tm[6] + tm[4] * tm[7]) + f2 * (tm[5] * tm[8]);
-                    const float eex = f0 * (tm[0] * tm[0] + tm[1] * tm[1]) + f2 * (tm[2] * tm[2]);
-                    const float eey = f0 * (tm[3] * tm[3] + tm[4] * tm[4]) + f2 * (tm[5] * tm[5]);
-                    const float ehx = sqrtf(fmaxf(0.0f, ecx * ecx - eex));
-                    const float ehy = sqrtf(fmaxf(0.0f, ecy * ecy - eey));
-                    const float mx = 0.05f + 1e-4f * (fabsf(ecx) + ehx);
-                    const float my = 0.05f + 1e-4f * (fabsf(ecy) + ehy);
-                    bx0 = fminf(bx0, ecx - ehx - mx); bx1 = fmaxf(bx1, ecx + ehx + mx);
-                    by0 = fminf(by0, ecy - ehy - my); by1 = fmaxf(by1, ecy + ehy + my);
-                    if (!(ecx == ecx) || !(ecy == ecy) || !(ehx == ehx) || !(ehy == ehy)) {
-                        bx0 = by0 = -3.0e38f; bx1 = by1 = 3.0e38f;
+                const float r2d = r2 * 1.41421366f;
+                ext[0] = -r2; ext[1] = r2; ext[2] = -r2; ext[3] = r2; ext[4] = -r2d; ext[5] = r2d; ext[6] = -r2d; ext[7] = r2d;
+                const double wxy = Twx * Twx + Twy * Twy, wz2 = Twz * Twz;
+                bool bounded = tm[8] > 0.0f && wz2 > 1.05 * (double)tau * wxy;
+                if (bounded) {
+                    const double d = (double)tau * wxy - wz2;
+                    const double f0 = (double)tau / d, f2 = -1.0 / d;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        // direction n: T_n = n.x Tu' + n.y Tv'
+                        const double nx = 1.0 - (k == 1), ny = (k == 0) ? 0.0 : (k == 3 ? -1.0 : 1.0);
+                        const double ax = nx * Tux + ny * Tvx, ay = nx * Tuy + ny * Tvy, az = nx * Tuz + ny * Tvz;
+                        const double ec = f0 * (ax * Twx + ay * Twy) + f2 * (az * Twz);
+                        const double ee = f0 * (ax * ax + ay * ay) + f2 * (az * az);
+                        const double eh = sqrt(fmax(0.0, ec * ec - ee));
+                        const double mg = 0.05 + 1e-5 * (fabs(ec) + eh);
+                        if (!(ec == ec) || !(eh == eh)) bounded = false;
+                        ext[2 * k] = fminf(ext[2 * k], (float)(ec - eh - mg));
+                        ext[2 * k + 1] = fmaxf(ext[2 * k + 1], (float)(ec + eh + mg));
                     }
-                } else {
-                    bx0 = by0 = -3.0e38f; bx1 = by1 = 3.0e38f;  // unbounded conic: never culled
+                }
+                if (!bounded) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) { ext[2 * k] = -3.0e38f; ext[2 * k + 1] = 3.0e38f; }   // unbounded conic: never culled
                 }
             }
-            // record -> the warp's shared-memory panel (7-quad stride: conflict-free); the warp then
-            // streams its 32 records (3 KB contiguous) to HBM with fully coalesced 128-bit stores
-            float4* r = s_sh + warp * 32 * kShRowQuads + lane * 7;
-            r[0] = make_float4(tm[0], tm[1], tm[2], tm[3]);
-            r[1] = make_float4(tm[4], tm[5], tm[6], tm[7]);
-            r[2] = make_float4(tm[8], cx, cy, opa);
-            r[3] = make_float4(nrm[0], nrm[1], nrm[2], pvz);
-            r[4] = make_float4(rgb[0], rgb[1], rgb[2], __uint_as_float((uint32_t)idx));   // .w: splat index (bits)
-            r[5] = make_float4(bx0, by0, bx1, by1);
+            const float cu = cx + cy, cv = cx - cy;
+            // records -> the warp's shared-memory panel (11-quad stride: conflict-free); the warp then
+            // streams its 32 render records (4 KB contiguous) and 32 transform records (1.5 KB) to HBM
+            // with fully coalesced 128-bit stores
+            float4* r = s_sh + warp * 32 * kShRowQuads + lane * 11;
+            r[0] = make_float4((float)P1x, (float)P1y, (float)P1z, cx);
+            r[1] = make_float4((float)P2x, (float)P2y, (float)P2z, cy);
+            r[2] = make_float4((float)Pcx, (float)Pcy, (float)Pcz, opa);
+            r[3] = make_float4(nrm[0], nrm[1], nrm[2], tm[8]);
+            r[4] = make_float4(rgb[0], rgb[1], rgb[2], (float)det);
+            r[5] = make_float4(tm[6], tm[7], __uint_as_float((uint32_t)idx), pvz);
+            r[6] = make_float4(cx + ext[0], cy + ext[2], cx + ext[1], cy + ext[3]);
+            r[7] = make_float4(cu + ext[4], cu + ext[5], cv + ext[6], cv + ext[7]);
+            r[8] = make_float4(tm[0], tm[1], tm[2], tm[3]);
+            r[9] = make_float4(tm[4], tm[5], tm[6], tm[7]);
+            r[10] = make_float4(tm[8], cx, cy, pvz);
         }
     }
     {
@@ -377,8 +401,13 @@ __global__ void __launch_bounds__(kPreBlock, 8) preprocess_fwd_kernel(PreFwdPara
         const float4* src = s_sh + warp * 32 * kShRowQuads;
         float4* dst = p.rec + (size_t)warp_first * kRecQuads;
         for (int f = lane; f < nrows * kRecQuads; f += 32) {
-            const int row = f / kRecQuads, q = f - row * kRecQuads;
-            if ((vis_mask >> row) & 1u) dst[f] = src[row * 7 + q];
+            const int row = f >> 3, q = f & 7;
+            if ((vis_mask >> row) & 1u) dst[f] = src[row * 11 + q];
+        }
+        float4* dst2 = p.tmat + (size_t)warp_first * kTmQuads;
+        for (int f = lane; f < nrows * kTmQuads; f += 32) {
+            const int row = f / kTmQuads, q = f - row * kTmQuads;
+            if ((vis_mask >> row) & 1u) dst2[f] = src[row * 11 + 8 + q];
         }
     }
 

@@ -7,15 +7,19 @@
 // dL_dnormal[3], dL_dcolor[3].
 //
 // B200 design (not upstream's, which issues up to 16 global float atomics per (pixel,splat)):
-//  * same 96-byte records / 8x4 warp footprints / bbox ballot culling as the forward (exact);
-//  * the CTA starts at the largest last_contributor of its pixels, not at the end of the list;
-//  * per (warp, splat) the lanes that really contribute (on average ~9 of 32 at 1 M splats / 1080p,
-//    ncu profiles/r1) are compacted with a ballot: each writes its 21 partials as one row
-//    into a per-warp shared-memory panel, then 21 lanes each add one COLUMN of the panel and issue
-//    ONE red.global.add.f32 into the splat's 96-byte gradient record (layout: common.cuh; the
-//    homography gradient is carried as the sums A, Bx, By, Z and finished in preprocess backward).  Work scales with the number
-//    of contributing lanes (a 32-lane shuffle butterfly cost 108 instructions per splat regardless),
-//    and global atomics drop from 18 per (pixel,splat) to 18 per (warp,splat), contiguous.
+//  * same 128-byte records / staging-time footprint classification / 8x4 warp footprints / affine
+//    ray-splat intersection as the forward (render_fwd.cu); the classification is exact, and the
+//    per-pair decisions are bit-identical to the forward's (same inline evaluation);
+//  * the CTA starts at the largest last_contributor of its pixels, not at the end of the list, and for
+//    all but crowded tiles the whole replay is staged in one round (no block barrier in the hit loop);
+//  * A.4's eight suffix recurrences are collapsed into ONE accumulator S (see below);
+//  * per (warp, splat) the lanes that really contribute (~9 of 32 at 1 M splats / 1080p) are compacted
+//    with a ballot: each writes its 22 partials as one row of a per-warp shared-memory panel, then 22
+//    lanes each add one COLUMN of the panel (a fall-through ladder entered at the row count: two
+//    instructions per row, no loop) and issue ONE red.global.add.f32 into the splat's 96-byte gradient
+//    record (layout: common.cuh; the homography gradient is carried as the sums A, Bx, By, Z and finished
+//    in preprocess backward).  Global atomics drop from 18 per (pixel,splat) to 18 per (warp,splat),
+//    contiguous.
 #include "render_common.cuh"
 #include "kernels.h"
 #include "profile.h"
@@ -26,15 +30,74 @@ namespace surfel {
 #define SURFEL_BWD_BLOCKS 4
 #endif
 #ifndef SURFEL_BWD_BATCH
-#define SURFEL_BWD_BATCH 192
+#define SURFEL_BWD_BATCH 352
 #endif
-constexpr int kBatchB = SURFEL_BWD_BATCH;   // 18 KB of records + 28 KB panel fit the 48 KB static limit
-constexpr int kPanelRow = 28;                     // 21 used floats, 7-quad stride (odd: conflict-free STS.128)
+constexpr int kBatchB = SURFEL_BWD_BATCH;         // multiple of 32
+constexpr int kGroupsB = kBatchB / 32;
+constexpr int kPanelRow = 24;                     // 22 used floats; rows 4 apart share banks (rarely both live in a quarter warp)
+constexpr int kPanelBytes = 8 * 32 * kPanelRow * 4;
+constexpr int kRecBytesB = kRecQuadsFwd * kBatchB * 16;        // the backward stages the same five quads as the forward
+constexpr int kBwdSmemBytes = kRecBytesB + kBatchB * 4 + kPanelBytes + 8 * kGroupsB * 4 + 32;
+
+// acc = sum of the first `cnt` (1..32) rows of this lane's panel column: a fall-through ladder entered
+// through ONE indexed branch (brx.idx; a C++ switch is lowered to a tree of compares by nvcc) — one LDS and
+// one FADD per row, no loop, no per-row control flow.
+static_assert(kPanelRow * 4 == 96, "the ladder below hard-codes the 96-byte row stride");
+__device__ __forceinline__ float column_sum(uint32_t a, int cnt) {
+    float acc = 0.0f;
+#ifdef SURFEL_BWD_LOOP_SUM
+    for (int r = 0; r < cnt; r++) acc += lds32(a + r * kPanelRow * 4);
+    return acc;
+#endif
+    asm volatile(
+        "{\n"
+        "    .reg .f32 t;\n"
+        "    ts: .branchtargets L1, L2, L3, L4, L5, L6, L7, L8, L9, L10, L11, L12, L13, L14, L15, L16, L17, L18, L19, L20, L21, L22, L23, L24, L25, L26, L27, L28, L29, L30, L31, L32;\n"
+        "    brx.idx %2, ts;\n"
+        "L32: ld.shared.f32 t, [%1 + 2976]; add.f32 %0, %0, t;\n"
+        "L31: ld.shared.f32 t, [%1 + 2880]; add.f32 %0, %0, t;\n"
+        "L30: ld.shared.f32 t, [%1 + 2784]; add.f32 %0, %0, t;\n"
+        "L29: ld.shared.f32 t, [%1 + 2688]; add.f32 %0, %0, t;\n"
+        "L28: ld.shared.f32 t, [%1 + 2592]; add.f32 %0, %0, t;\n"
+        "L27: ld.shared.f32 t, [%1 + 2496]; add.f32 %0, %0, t;\n"
+        "L26: ld.shared.f32 t, [%1 + 2400]; add.f32 %0, %0, t;\n"
+        "L25: ld.shared.f32 t, [%1 + 2304]; add.f32 %0, %0, t;\n"
+        "L24: ld.shared.f32 t, [%1 + 2208]; add.f32 %0, %0, t;\n"
+        "L23: ld.shared.f32 t, [%1 + 2112]; add.f32 %0, %0, t;\n"
+        "L22: ld.shared.f32 t, [%1 + 2016]; add.f32 %0, %0, t;\n"
+        "L21: ld.shared.f32 t, [%1 + 1920]; add.f32 %0, %0, t;\n"
+        "L20: ld.shared.f32 t, [%1 + 1824]; add.f32 %0, %0, t;\n"
+        "L19: ld.shared.f32 t, [%1 + 1728]; add.f32 %0, %0, t;\n"
+        "L18: ld.shared.f32 t, [%1 + 1632]; add.f32 %0, %0, t;\n"
+        "L17: ld.shared.f32 t, [%1 + 1536]; add.f32 %0, %0, t;\n"
+        "L16: ld.shared.f32 t, [%1 + 1440]; add.f32 %0, %0, t;\n"
+        "L15: ld.shared.f32 t, [%1 + 1344]; add.f32 %0, %0, t;\n"
+        "L14: ld.shared.f32 t, [%1 + 1248]; add.f32 %0, %0, t;\n"
+        "L13: ld.shared.f32 t, [%1 + 1152]; add.f32 %0, %0, t;\n"
+        "L12: ld.shared.f32 t, [%1 + 1056]; add.f32 %0, %0, t;\n"
+        "L11: ld.shared.f32 t, [%1 + 960]; add.f32 %0, %0, t;\n"
+        "L10: ld.shared.f32 t, [%1 + 864]; add.f32 %0, %0, t;\n"
+        "L9: ld.shared.f32 t, [%1 + 768]; add.f32 %0, %0, t;\n"
+        "L8: ld.shared.f32 t, [%1 + 672]; add.f32 %0, %0, t;\n"
+        "L7: ld.shared.f32 t, [%1 + 576]; add.f32 %0, %0, t;\n"
+        "L6: ld.shared.f32 t, [%1 + 480]; add.f32 %0, %0, t;\n"
+        "L5: ld.shared.f32 t, [%1 + 384]; add.f32 %0, %0, t;\n"
+        "L4: ld.shared.f32 t, [%1 + 288]; add.f32 %0, %0, t;\n"
+        "L3: ld.shared.f32 t, [%1 + 192]; add.f32 %0, %0, t;\n"
+        "L2: ld.shared.f32 t, [%1 + 96]; add.f32 %0, %0, t;\n"
+        "L1: ld.shared.f32 t, [%1 + 0]; add.f32 %0, %0, t;\n"
+        "}\n"
+        : "+f"(acc) : "r"(a), "r"(cnt - 1));
+    return acc;
+}
 
 __global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(RenderParams p) {
-    __shared__ float4 s_rec[kRecQuads * kBatchB];            // [quad][slot]; quad 4 .w carries the splat id
-    __shared__ __align__(16) float s_panel[8 * 32 * kPanelRow];
-    __shared__ uint32_t s_max[8];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* s_rec = reinterpret_cast<float4*>(smem_raw);                                     // [quad][slot]
+    uint32_t* s_id = reinterpret_cast<uint32_t*>(smem_raw + kRecBytesB);                     // [slot] splat index
+    float* s_panel = reinterpret_cast<float*>(smem_raw + kRecBytesB + kBatchB * 4);
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem_raw + kRecBytesB + kBatchB * 4 + kPanelBytes);  // [warp][group]
+    uint32_t* s_max = s_mask + 8 * kGroupsB;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = blockIdx.x, ty = blockIdx.y + p.row0;
@@ -43,14 +106,15 @@ __global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(Rend
     const int px = tx * kBlockX + lx, py = ty * kBlockY + ly;
     const bool inside = px < p.W && py < p.H;
     const float pxf = (float)px, pyf = (float)py;
-    const float fx0 = (float)(tx * kBlockX + ((warp & 1) << 3)), fx1 = fx0 + 7.0f;
-    const float fy0 = (float)(ty * kBlockY + ((warp >> 1) << 2)), fy1 = fy0 + 3.0f;
+    const float ox = (float)(tx * kBlockX), oy = (float)(ty * kBlockY);
     const uint2 range = p.ranges[ty * p.gx + tx];
     const size_t HW = (size_t)p.H * p.W;
     const size_t pix = (size_t)py * p.W + px;
     const uint32_t rec_base = smem_u32(s_rec);
-    const uint32_t panel_base = smem_u32(s_panel) + warp * (32 * kPanelRow * 4);
-    const unsigned lt_mask = (1u << lane) - 1u;
+    uint32_t panel_base = smem_u32(s_panel) + warp * (32 * kPanelRow * 4);
+    const uint32_t id_base = smem_u32(s_id);
+    const uint32_t mask_base = smem_u32(s_mask) + (uint32_t)warp * (kGroupsB * 4);
+    unsigned lt_mask = (1u << lane) - 1u;
 
     float T_final = 0, final_D = 0, final_D2 = 0;
     uint32_t last_contributor = 0, median_contributor = 0;
@@ -71,6 +135,7 @@ __global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(Rend
     const float final_A = 1.0f - T_final;
     const float bgT = -T_final * ((__ldg(p.bg + 0) * dpix0 + __ldg(p.bg + 1) * dpix1) + __ldg(p.bg + 2) * dpix2);
     const uint32_t median_index = median_contributor - 1u;   // 0xFFFFFFFE when there is none
+    const bool quirk = p.lowpass_quirk != 0;
 
     // warp / CTA extent of the replay
     uint32_t warp_max = last_contributor;
@@ -94,56 +159,78 @@ __global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(Rend
     for (int end = (int)cta_max; end > 0; end -= kBatchB) {
         const int n = min(kBatchB, end);
         const int start = end - n;
-        __syncthreads();
-        if (tid < n) {
-            const uint32_t id = p.point_list[range.x + start + tid];
-            const float4* r = p.rec + (size_t)id * kRecQuads;
+        if (end != (int)cta_max) __syncthreads();         // previous round's reads before this refill
+        // ---- stage + classify (as in the forward) ----
 #pragma unroll
-            for (int q = 0; q < kRecQuads; q++) {
-                float4 v = __ldg(r + q);
-                if (q == 4) v.w = __uint_as_float(id);
-                s_rec[q * kBatchB + tid] = v;
+        for (int k = 0; k < (kBatchB + 255) / 256; k++) {
+            const int slot = k * 256 + tid;
+            if (k * 256 + (warp << 5) >= n) break;                       // warp-uniform
+            uint32_t m8 = 0;
+            if (slot < n) {
+                const uint32_t id = __ldg(p.point_list + range.x + start + slot);
+                const float4* r = p.rec + (size_t)id * kRecQuads;
+                const float4 bb = __ldg(r + 6), dg = __ldg(r + 7);
+#ifdef SURFEL_STAGE_LDG
+#pragma unroll
+                for (int q = 0; q < kRecQuadsFwd; q++) s_rec[q * kBatchB + slot] = __ldg(r + q);
+#else
+#pragma unroll
+                for (int q = 0; q < kRecQuadsFwd; q++) cp_async16(rec_base + (uint32_t)(q * kBatchB + slot) * 16u, r + q);
+#endif
+                s_id[slot] = id;
+                m8 = classify_footprints(bb, dg, ox, oy);
             }
+            uint32_t keep = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                const uint32_t b = __ballot_sync(0xffffffffu, (m8 >> w) & 1u);
+                if (lane == w) keep = b;
+            }
+            if (lane < 8) s_mask[lane * kGroupsB + k * 8 + warp] = keep;
         }
+        cp_async_wait_all();
         __syncthreads();
-        if ((int)warp_max <= start) continue;   // nothing of this batch reaches this warp's pixels
+        if ((int)warp_max <= start) continue;   // nothing of this round reaches this warp's pixels
 
-        for (int c = ((n - 1) >> 5) << 5; c >= 0; c -= 32) {
-            const int slot = c + lane;
-            bool hit = false;
-            if (slot < n && (uint32_t)(start + slot) < warp_max) {
-                const float4 bb = lds128(rec_base + (5 * kBatchB + slot) * 16);
-                hit = bb.x <= fx1 && bb.z >= fx0 && bb.y <= fy1 && bb.w >= fy0;
-            }
-            unsigned m = __ballot_sync(0xffffffffu, hit);
-            uint32_t gb = rec_base + (uint32_t)c * 16u;
-            asm volatile("" : "+r"(gb));      // keep it in a register (else re-derived from SR_CgaCtaId per hit)
-            const int own = (int)last_contributor - (start + c);      // bits below `own` are this pixel's
-            const int med = (int)median_index - (start + c);
+        const int top = min(n, (int)warp_max - start);            // slots [0, top) can contribute
+        for (int g = (top - 1) >> 5; g >= 0; g--) {
+            unsigned m = lds32u(mask_base + (uint32_t)g * 4u) & low_mask((uint32_t)(top - (g << 5)));
+            uint32_t gb = rec_base + (uint32_t)(g << 5) * 16u, idb = id_base + (uint32_t)(g << 5) * 4u;
+            // keep the shared-memory bases in registers (else re-derived from SR_CgaCtaId / SR_TID per hit)
+            asm volatile("" : "+r"(gb), "+r"(idb), "+r"(panel_base), "+r"(lt_mask));
+            const int own = (int)last_contributor - (start + (g << 5));      // bits below `own` are this pixel's
+            const int med = (int)median_index - (start + (g << 5));
             while (m) {
                 const uint32_t j = high_bit(m);                       // back to front
                 m &= low_mask(j);
                 const uint32_t ra = gb + j * 16u;
                 const float4 q0 = lds128(ra), q1 = lds128(ra + kBatchB * 16), q2 = lds128(ra + 2 * kBatchB * 16);
                 PairEval e;
-                const bool active = (int)j < own && eval_pair(pxf, pyf, q0, q1, q2, e);
+                bool active = eval_pair(pxf, pyf, q0, q1, q2, e) && (int)j < own;
+                float4 q3, q4;
+                float depth = 0.0f;
+                const bool use3d = e.rho3d <= e.rho2d;
+                if (active) {
+                    q3 = lds128(ra + 3 * kBatchB * 16); q4 = lds128(ra + 4 * kBatchB * 16);
+                    depth = use3d ? q4.w * e.inv_pz : q3.w;      // det T / p.z, or Tw.z in the low-pass branch
+                    active = !(depth < kNear);
+                }
                 const unsigned am = __ballot_sync(0xffffffffu, active);
                 if (am == 0u) continue;
 
                 if (active) {
-                    const float4 q3 = lds128(ra + 3 * kBatchB * 16), q4 = lds128(ra + 4 * kBatchB * 16);
                     const float G = e.G, alpha = e.alpha;
                     const float one_m = 1.0f - alpha;
                     const float inv1ma = fast_rcp(one_m);
                     T = T * inv1ma;
                     const float w = alpha * T;
-                    const float inv_d = fast_rcp(e.depth);
+                    const float inv_d = fast_rcp(depth);
                     const float m_d = kMScale * (1.0f - kNear * inv_d);
                     const float dmd_dd = kDmScale * inv_d * inv_d;
                     const float dL_dweight = (final_D2 + m_d * m_d * final_A - 2.0f * m_d * final_D) * dL_dreg;
                     float v = dL_dweight + dL_daccum;
                     v = fmaf(q4.x, dpix0, v); v = fmaf(q4.y, dpix1, v); v = fmaf(q4.z, dpix2, v);
-                    v = fmaf(e.depth, dL_ddepth, v);
+                    v = fmaf(depth, dL_ddepth, v);
                     v = fmaf(q3.x, dN0, v); v = fmaf(q3.y, dN1, v); v = fmaf(q3.z, dN2, v);
                     const float dL_dalpha = T * v - (S - bgT) * inv1ma;
                     S = fmaf(w, v, S);
@@ -151,38 +238,35 @@ __global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(Rend
                     dL_dz += 2.0f * w * (m_d * final_A - final_D) * dL_dreg * dmd_dd;
                     const float dL_dG = q2.w * dL_dalpha;
                     dL_dz += w * dL_ddepth;
-                    float ax = 0, ay = 0, az = 0, zx = 0, zy = 0, m2x = 0, m2y = 0;
-                    if (e.use3d) {
-                        const float Twx = q1.z, Twy = q1.w;
-                        const float nG = -G * dL_dG;
-                        const float dsx = nG * e.sx + dL_dz * Twx;
-                        const float dsy = nG * e.sy + dL_dz * Twy;
-                        ax = dsx * e.inv_pz; ay = dsy * e.inv_pz;
-                        az = -(ax * e.sx + ay * e.sy);
-                        zx = dL_dz * e.sx; zy = dL_dz * e.sy;
+                    float ax = 0, ay = 0, az = 0, zd = 0, zx = 0, zy = 0, zz = 0, m2x = 0, m2y = 0;
+                    if (use3d) {
+                        // G = exp(-0.5 |s|^2), s = p.xy / p.z, depth = det T / p.z
+                        const float t = -G * dL_dG * e.inv_pz;
+                        ax = t * e.sx; ay = t * e.sy;
+                        zd = dL_dz * e.inv_pz;                                   // dL/d(det T)
+                        az = -fmaf(ax, e.sx, fmaf(ay, e.sy, zd * depth));        // dL/dp.z
                     } else {
-                        const float gg = -G * kFilterInvSquare * dL_dG;
+                        // upstream: dL_dmean2D += dL_dG * (-G * FilterInvSquare * d), d = c - pixel = -(dx, dy)
+                        const float gg = G * kFilterInvSquare * dL_dG;
                         m2x = gg * e.dx; m2y = gg * e.dy;
-                        if (p.lowpass_quirk) { zx = e.sx * dL_dz; zy = e.sy * dL_dz; }
+                        zz = dL_dz;
+                        // upstream "Propagate the gradients of depth" in this branch: dL_dTw += (s.x, s.y, 1) dL_dz
+                        if (quirk) { zx = e.sx * dL_dz; zy = e.sy * dL_dz; }
                     }
-                    const float ndx = -e.dx, ndy = -e.dy;      // pixel - AABB centre
                     // one row per contributing lane (rows are compacted: ballot prefix)
-                    const uint32_t row = panel_base + __popc(am & lt_mask) * (kPanelRow * 4);
-                    sts128(row, make_float4(ax, ay, az, ndx * ax));
-                    sts128(row + 16, make_float4(ndx * ay, ndx * az, ndy * ax, ndy * ay));
-                    sts128(row + 32, make_float4(ndy * az, zx, zy, dL_dz));
-                    sts128(row + 48, make_float4(m2x, m2y, G * dL_dalpha, w * dN0));
-                    sts128(row + 64, make_float4(w * dN1, w * dN2, w * dpix0, w * dpix1));
-                    sts32(row + 80, w * dpix2);
+                    const uint32_t ro = panel_base + (uint32_t)__popc(am & lt_mask) * (kPanelRow * 4);
+                    sts128(ro, make_float4(ax, ay, az, e.dx * ax));
+                    sts128(ro + 16, make_float4(e.dx * ay, e.dx * az, e.dy * ax, e.dy * ay));
+                    sts128(ro + 32, make_float4(e.dy * az, zd, zx, zy));
+                    sts128(ro + 48, make_float4(zz, m2x, m2y, G * dL_dalpha));
+                    sts128(ro + 64, make_float4(w * dN0, w * dN1, w * dN2, w * dpix0));
+                    sts64(ro + 80, w * dpix1, w * dpix2);
                 }
                 __syncwarp();
                 if (lane < kGradUsed) {
-                    const int nact = __popc(am);
-                    uint32_t a = panel_base + lane * 4;
-                    float acc = 0.0f;
-                    for (int r = 0; r < nact; r++, a += kPanelRow * 4) acc += lds32(a);
+                    const float acc = column_sum(panel_base + lane * 4, __popc(am));
                     if (acc != 0.0f) {
-                        const uint32_t id = __float_as_uint(lds32(ra + 4 * kBatchB * 16 + 12));
+                        const uint32_t id = lds32u(idb + j * 4u);
                         atomicAdd(p.grad_rec + (size_t)id * kGradFloats + lane, acc);
                     }
                 }
@@ -195,9 +279,15 @@ __global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(Rend
 int launch_render_bwd(const RenderParams& p, cudaStream_t stream) {
     const int rows = p.row1 - p.row0;
     if (rows <= 0 || p.gx <= 0) return 0;
+    static bool attr_set[kMaxDevices] = {};
+    const int slot = current_device_slot();
+    if (slot < 0 || !attr_set[slot]) {
+        SURFEL_CUDA_OK(cudaFuncSetAttribute(render_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBwdSmemBytes));
+        if (slot >= 0) attr_set[slot] = true;
+    }
     dim3 grid(p.gx, rows);
     LaunchScope scope(kStRenderBwd, stream);
-    render_bwd_kernel<<<grid, 256, 0, stream>>>(p);
+    render_bwd_kernel<<<grid, 256, kBwdSmemBytes, stream>>>(p);
     SURFEL_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -10,12 +10,11 @@
 namespace surfel {
 
 struct PairEval {
-    float kx, ky, kz, lx, ly, lz;   // k = px*Tw - Tu, l = py*Tw - Tv
+    float dx, dy;                   // pixel - splat screen position c (note: upstream's d = c - pixel)
     float pz, inv_pz;               // cross(k,l).z and its reciprocal
     float sx, sy;                   // splat-space intersection
-    float dx, dy;                   // xy - pixel
-    float depth, G, alpha;
-    bool use3d;                     // rho3d <= rho2d (ray-splat branch), else low-pass branch
+    float rho3d, rho2d;             // ray-splat and low-pass squared distances
+    float G, alpha;
 };
 
 __device__ __forceinline__ float fast_rcp(float x) {
@@ -29,36 +28,52 @@ __device__ __forceinline__ float fast_ex2(float x) {
     return r;
 }
 
-// q0 = (Tu.x,Tu.y,Tu.z,Tv.x) q1 = (Tv.y,Tv.z,Tw.x,Tw.y) q2 = (Tw.z, xy.x, xy.y, opacity)
-// Returns false when one of the A.3 `continue` tests that precede the transmittance test fires.
+// Per-(pixel, splat) evaluation up to alpha, from the affine form of the ray-splat intersection
+// (record layout: common.cuh):  p = Pc + dx P1 + dy P2,  s = p.xy / p.z,  rho3d = |s|^2,
+// rho2d = 2 |d|^2,  alpha = min(0.99, opacity * exp(-0.5 min(rho3d, rho2d))).
+//   q0 = (P1.x, P1.y, P1.z, c.x)   q1 = (P2.x, P2.y, P2.z, c.y)   q2 = (Pc.x, Pc.y, Pc.z, opacity)
+// Returns false when the pair is skipped by A.3's `p.z == 0` or `alpha < 1/255` tests.  The remaining
+// A.3 `continue` tests: `power > 0` cannot fire (rho >= 0 or NaN, and NaN compares false upstream as
+// well); `depth < near` is applied by the callers once the depth is known (live lanes only).
+// Every operation is an explicit round-to-nearest intrinsic so that forward and backward (separate
+// translation units) take bit-identical decisions for a pair.
 __device__ __forceinline__ bool eval_pair(float pxf, float pyf, const float4& q0, const float4& q1,
                                           const float4& q2, PairEval& e) {
-    const float Twx = q1.z, Twy = q1.w, Twz = q2.x;
-    e.kx = __fmaf_rn(pxf, Twx, -q0.x); e.ky = __fmaf_rn(pxf, Twy, -q0.y); e.kz = __fmaf_rn(pxf, Twz, -q0.z);
-    e.lx = __fmaf_rn(pyf, Twx, -q0.w); e.ly = __fmaf_rn(pyf, Twy, -q1.x); e.lz = __fmaf_rn(pyf, Twz, -q1.y);
-    const float ppx = __fmaf_rn(e.ky, e.lz, -__fmul_rn(e.kz, e.ly));
-    const float ppy = __fmaf_rn(e.kz, e.lx, -__fmul_rn(e.kx, e.lz));
-    e.pz = __fmaf_rn(e.kx, e.ly, -__fmul_rn(e.ky, e.lx));
-    // The A.3 `continue` tests are folded into one predicate instead of four early exits: a warp
-    // practically never fails one of the first three on all 32 lanes, so as branches they only cost
-    // issue slots and branch-resolve stalls.  Lanes that fail keep computing on inf/NaN, harmlessly.
-    bool ok = e.pz != 0.0f;
-    const float inv = fast_rcp(e.pz);
-    e.inv_pz = inv;
-    e.sx = __fmul_rn(ppx, inv); e.sy = __fmul_rn(ppy, inv);
-    const float rho3d = __fmaf_rn(e.sx, e.sx, __fmul_rn(e.sy, e.sy));
-    e.dx = __fsub_rn(q2.y, pxf); e.dy = __fsub_rn(q2.z, pyf);
-    const float rho2d = __fmul_rn(kFilterInvSquare, __fmaf_rn(e.dx, e.dx, __fmul_rn(e.dy, e.dy)));
-    e.use3d = rho3d <= rho2d;
-    const float rho = fminf(rho3d, rho2d);
-    e.depth = e.use3d ? __fadd_rn(__fmaf_rn(e.sx, Twx, __fmul_rn(e.sy, Twy)), Twz) : Twz;
-    ok &= !(e.depth < kNear);
-    const float power = __fmul_rn(-0.5f, rho);
-    ok &= !(power > 0.0f);
-    e.G = fast_ex2(__fmul_rn(power, 1.4426950408889634f));
+    e.dx = __fsub_rn(pxf, q0.w); e.dy = __fsub_rn(pyf, q1.w);
+    const float ppx = __fmaf_rn(e.dy, q1.x, __fmaf_rn(e.dx, q0.x, q2.x));
+    const float ppy = __fmaf_rn(e.dy, q1.y, __fmaf_rn(e.dx, q0.y, q2.y));
+    e.pz = __fmaf_rn(e.dy, q1.z, __fmaf_rn(e.dx, q0.z, q2.z));
+    e.inv_pz = fast_rcp(e.pz);
+    e.sx = __fmul_rn(ppx, e.inv_pz); e.sy = __fmul_rn(ppy, e.inv_pz);
+    e.rho3d = __fmaf_rn(e.sx, e.sx, __fmul_rn(e.sy, e.sy));
+    const float h = __fmaf_rn(e.dx, e.dx, __fmul_rn(e.dy, e.dy));
+    e.rho2d = __fadd_rn(h, h);                                   // FilterInvSquare = 2
+    const float rho = fminf(e.rho3d, e.rho2d);
+    e.G = fast_ex2(__fmul_rn(rho, -0.72134752044448170368f));    // exp(-0.5 rho)
     e.alpha = fminf(kAlphaMax, __fmul_rn(q2.w, e.G));
-    ok &= !(e.alpha < kAlphaMin);
-    return ok;
+    return !(e.alpha < kAlphaMin) && e.pz != 0.0f;
+}
+
+// Classification of one splat against the eight 8x4 warp footprints of a 16x16 tile, done by the thread
+// that stages the splat's record (it has the record in registers): bit w of the result = the region
+// where the splat can reach alpha >= 1/255 (screen AABB q6 and diagonal extents q7, both conservative)
+// overlaps the footprint of warp w.  A miss is exact, not approximate: no pixel of that footprint can
+// pass A.3's alpha test, so the warp never evaluates the pair.  (ox, oy) = the tile's first pixel.
+__device__ __forceinline__ uint32_t classify_footprints(const float4& bb, const float4& dg, float ox, float oy) {
+    // relative to the tile origin every bound is a small constant
+    const float x0 = bb.x - ox, x1 = bb.z - ox, y0 = bb.y - oy, y1 = bb.w - oy;
+    const float ou = ox + oy, ov = ox - oy;
+    const float u0 = dg.x - ou, u1 = dg.y - ou, v0 = dg.z - ov, v1 = dg.w - ov;
+    uint32_t m = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+        const float fx0 = (float)((w & 1) << 3), fx1 = fx0 + 7.0f;
+        const float fy0 = (float)((w >> 1) << 2), fy1 = fy0 + 3.0f;
+        const bool hit = x0 <= fx1 && x1 >= fx0 && y0 <= fy1 && y1 >= fy0 &&
+                         u0 <= fx1 + fy1 && u1 >= fx0 + fy0 && v0 <= fx1 - fy0 && v1 >= fx0 - fy1;
+        m |= hit ? (1u << w) : 0u;
+    }
+    return m;
 }
 
 // Position of the highest set bit (FLO) and the mask of the bits below a position (BMSK): the hit
@@ -84,6 +99,11 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
     asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
     return v;
 }
+__device__ __forceinline__ float2 lds64(uint32_t addr) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void sts128(uint32_t addr, const float4& v) {
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
@@ -97,6 +117,20 @@ __device__ __forceinline__ float lds32(uint32_t addr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
     return v;
+}
+__device__ __forceinline__ uint32_t lds32u(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// 16-byte global -> shared copy that bypasses registers (LDGSTS): the staging threads of the render
+// kernels keep only the two culling quads of a record in registers.
+__device__ __forceinline__ void cp_async16(uint32_t smem_addr, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 // Warp footprint inside a 16x16 tile: 8 (x) by 4 (y) pixels; warp w sits at (w&1, w>>1).

@@ -5,14 +5,20 @@
 // view-space normal, median depth and the depth-distortion accumulator in one pass, saving
 // final_T / M1 / M2 / n_contrib / median_contributor for the backward.
 //
-// B200 design (not upstream's): the list is staged 256 splats at a time as 96-byte records
-// (6 x LDG.128 per splat -> conflict-free quad-planar shared memory).  Each warp owns an 8x4 pixel
-// footprint; its 32 lanes test 32 staged splats at once against the footprint using the splat's
-// conservative screen bbox (record quad 5), ballot the hits, and only the hit splats are evaluated
-// (warp-wide compaction).  A splat whose bbox misses the footprint cannot reach alpha >= 1/255 on
-// any of the warp's pixels, so skipping it is exact, not approximate; the contributor counter is
-// derived from the list position, so bookkeeping (n_contrib, median contributor) is unchanged.
-// Early termination is per warp (all 32 pixels done), then per CTA.
+// B200 design (not upstream's):
+//  * the tile's list is staged ONCE for all but crowded tiles (kBatch = 384 slots; the mean list at the
+//    headline workload is 292), so the hit loop runs without a block barrier; longer lists take further
+//    rounds;
+//  * staging thread t gathers splat t's 128-byte record: quads 0-4 go straight to quad-planar shared memory
+//    with cp.async (LDGSTS, no registers), the two culling quads into registers, where the thread classifies the splat against the
+//    eight 8x4 warp footprints of the tile (screen AABB + diagonal extents of the region where alpha can
+//    reach 1/255, render_common.cuh).  Ballots turn the classification into one 32-bit hit mask per
+//    (warp, 32-slot group) in shared memory;
+//  * each warp owns an 8x4 pixel footprint and evaluates only its hits: a miss cannot reach
+//    alpha >= 1/255 on any of the warp's pixels, so skipping it is exact, and the contributor counter is
+//    derived from the list position, so n_contrib / median contributor are unchanged.  Hit bits are
+//    peeled front to back with FLO/BMSK, the ray-splat intersection costs 6 FMA (affine form, common.cuh);
+//  * early termination per warp (all 32 pixels saturated), then per CTA.
 #include "render_common.cuh"
 #include "kernels.h"
 #include "profile.h"
@@ -20,13 +26,19 @@
 namespace surfel {
 
 #ifndef SURFEL_FWD_BATCH
-#define SURFEL_FWD_BATCH 256
+#define SURFEL_FWD_BATCH 384
 #endif
-constexpr int kBatch = SURFEL_FWD_BATCH;
+#ifndef SURFEL_FWD_BLOCKS
+#define SURFEL_FWD_BLOCKS 5
+#endif
+constexpr int kBatch = SURFEL_FWD_BATCH;          // multiple of 32
+constexpr int kGroups = kBatch / 32;
+constexpr int kFwdSmemBytes = kRecQuadsFwd * kBatch * 16 + 8 * kGroups * 4;
 
-template <bool kSlab>   // kSlab: also lay the staged records out in sorted order (TMA-backward variant only)
-__global__ void __launch_bounds__(256, 5) render_fwd_kernel(RenderParams p) {
-    __shared__ float4 s_rec[kRecQuads * kBatch];     // [quad][slot]
+__global__ void __launch_bounds__(256, SURFEL_FWD_BLOCKS) render_fwd_kernel(RenderParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4* s_rec = reinterpret_cast<float4*>(smem_raw);                                   // [quad][slot]
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem_raw + kRecQuadsFwd * kBatch * 16);  // [warp][group], bit-reversed
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tx = blockIdx.x, ty = blockIdx.y + p.row0;
@@ -35,13 +47,12 @@ __global__ void __launch_bounds__(256, 5) render_fwd_kernel(RenderParams p) {
     const int px = tx * kBlockX + lx, py = ty * kBlockY + ly;
     const bool inside = px < p.W && py < p.H;
     const float pxf = (float)px, pyf = (float)py;
-    // warp footprint (pixel-centre coordinates)
-    const float fx0 = (float)(tx * kBlockX + ((warp & 1) << 3)), fx1 = fx0 + 7.0f;
-    const float fy0 = (float)(ty * kBlockY + ((warp >> 1) << 2)), fy1 = fy0 + 3.0f;
+    const float ox = (float)(tx * kBlockX), oy = (float)(ty * kBlockY);
 
     const uint2 range = p.ranges[ty * p.gx + tx];
     const int total = (int)(range.y - range.x);
     const uint32_t rec_base = smem_u32(s_rec);
+    const uint32_t mask_base = smem_u32(s_mask) + (uint32_t)warp * (kGroups * 4);
     constexpr float kMScale = kFar / (kFar - kNear);
 
     float T = 1.0f, C0 = 0, C1 = 0, C2 = 0, N0 = 0, N1 = 0, N2 = 0, D = 0, M1 = 0, M2 = 0, dist = 0;
@@ -51,58 +62,73 @@ __global__ void __launch_bounds__(256, 5) render_fwd_kernel(RenderParams p) {
     bool warp_done = __all_sync(0xffffffffu, !inside);
 
     for (int base = 0; base < total; base += kBatch) {
-        // CTA-wide early out (also orders the previous batch's smem reads before this refill)
-        if (!__syncthreads_or(!warp_done)) break;
+        // CTA-wide early out (also orders the previous round's smem reads before this refill)
+        if (base > 0 && !__syncthreads_or(!warp_done)) break;
 
         const int n = min(kBatch, total - base);
-        if (tid < n) {
-            const uint32_t id = p.point_list[range.x + base + tid];
-            const float4* r = p.rec + (size_t)id * kRecQuads;
+        // ---- stage + classify: thread t takes slots t, t + 256, ... (whole warps stay together) ----
 #pragma unroll
-            for (int q = 0; q < kRecQuads; q++) s_rec[q * kBatch + tid] = __ldg(r + q);
-            if (kSlab) {
-                float4* dst = p.slab + (size_t)(range.x + base + tid) * kRecQuads;
+        for (int k = 0; k < (kBatch + 255) / 256; k++) {
+            const int slot = k * 256 + tid;
+            if (k * 256 + (warp << 5) >= n) break;                       // warp-uniform
+            uint32_t m8 = 0;
+            if (slot < n) {
+                const uint32_t id = __ldg(p.point_list + range.x + base + slot);
+                const float4* r = p.rec + (size_t)id * kRecQuads;
+                const float4 bb = __ldg(r + 6), dg = __ldg(r + 7);
+#ifdef SURFEL_STAGE_LDG
 #pragma unroll
-                for (int q = 0; q < kRecQuads; q++) dst[q] = s_rec[q * kBatch + tid];
+                for (int q = 0; q < kRecQuadsFwd; q++) s_rec[q * kBatch + slot] = __ldg(r + q);
+#else
+#pragma unroll
+                for (int q = 0; q < kRecQuadsFwd; q++) cp_async16(rec_base + (uint32_t)(q * kBatch + slot) * 16u, r + q);
+#endif
+                m8 = classify_footprints(bb, dg, ox, oy);
             }
+            uint32_t keep = 0;
+#pragma unroll
+            for (int w = 0; w < 8; w++) {
+                const uint32_t b = __ballot_sync(0xffffffffu, (m8 >> w) & 1u);
+                if (lane == w) keep = b;
+            }
+            // bit 31 = first slot of the group: taking the highest set bit first walks the hits front to back
+            if (lane < 8) s_mask[lane * kGroups + k * 8 + warp] = __brev(keep);
         }
+        cp_async_wait_all();
         __syncthreads();
 
         if (!warp_done) {
-            for (int c = 0; c < n; c += 32) {
-                const int slot = c + lane;
-                bool hit = false;
-                if (slot < n) {
-                    const float4 bb = lds128(rec_base + (5 * kBatch + slot) * 16);
-                    hit = bb.x <= fx1 && bb.z >= fx0 && bb.y <= fy1 && bb.w >= fy0;
-                }
-                // bit 31 = slot c: taking the highest set bit first walks the hits front to back
-                unsigned m = __brev(__ballot_sync(0xffffffffu, hit));
+            const int ngroups = (n + 31) >> 5;
+            for (int g = 0; g < ngroups; g++) {
+                unsigned m = lds32u(mask_base + (uint32_t)g * 4u);
                 // The hit loop holds no warp-synchronous operation, so finished pixels simply skip it
                 // and a pixel that saturates leaves it early.  "Finished" is the top bit of
                 // last_contributor (lists are far shorter than 2^31).
                 if ((int)last_contributor >= 0) {
-                    const uint32_t g31 = rec_base + (uint32_t)(c + 31) * 16u;
-                    const uint32_t k32 = (uint32_t)(base + c + 32);
+                    const uint32_t g31 = rec_base + (uint32_t)(g * 32 + 31) * 16u;
+                    const uint32_t k32 = (uint32_t)(base + g * 32 + 32);
                     while (m) {
-                        const uint32_t hb = high_bit(m);               // slot c + 31 - hb
+                        const uint32_t hb = high_bit(m);               // slot g*32 + 31 - hb
                         m &= low_mask(hb);
                         const uint32_t ra = g31 - hb * 16u;
                         const float4 q0 = lds128(ra), q1 = lds128(ra + kBatch * 16), q2 = lds128(ra + 2 * kBatch * 16);
                         PairEval e;
                         if (!eval_pair(pxf, pyf, q0, q1, q2, e)) continue;
+                        const float4 q3 = lds128(ra + 3 * kBatch * 16), q4 = lds128(ra + 4 * kBatch * 16);
+                        // ray-splat depth = w of the intersection = det T / p.z; low-pass branch: Tw.z
+                        const float depth = (e.rho3d <= e.rho2d) ? q4.w * e.inv_pz : q3.w;
+                        if (depth < kNear) continue;
                         const float test_T = T * (1.0f - e.alpha);
                         if (test_T < kTMin) { last_contributor |= 0x80000000u; break; }
                         const uint32_t contributor = k32 - hb;   // 1-based list position
-                        const float4 q3 = lds128(ra + 3 * kBatch * 16), q4 = lds128(ra + 4 * kBatch * 16);
                         const float w = e.alpha * T;
                         const float A = 1.0f - T;
-                        const float mm = kMScale * (1.0f - kNear * fast_rcp(e.depth));
+                        const float mm = kMScale * (1.0f - kNear * fast_rcp(depth));
                         dist += (mm * mm * A + M2 - 2.0f * mm * M1) * w;
-                        D += e.depth * w;
+                        D += depth * w;
                         M1 += mm * w;
                         M2 += mm * mm * w;
-                        if (T > 0.5f) { median_depth = e.depth; median_contributor = contributor; }
+                        if (T > 0.5f) { median_depth = depth; median_contributor = contributor; }
                         N0 += q3.x * w; N1 += q3.y * w; N2 += q3.z * w;
                         C0 += q4.x * w; C1 += q4.y * w; C2 += q4.z * w;
                         T = test_T;
@@ -135,10 +161,15 @@ __global__ void __launch_bounds__(256, 5) render_fwd_kernel(RenderParams p) {
 int launch_render_fwd(const RenderParams& p, cudaStream_t stream) {
     const int rows = p.row1 - p.row0;
     if (rows <= 0 || p.gx <= 0) return 0;
+    static bool attr_set[kMaxDevices] = {};
+    const int slot = current_device_slot();
+    if (slot < 0 || !attr_set[slot]) {
+        SURFEL_CUDA_OK(cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+        if (slot >= 0) attr_set[slot] = true;
+    }
     dim3 grid(p.gx, rows);
     LaunchScope scope(kStRenderFwd, stream);
-    if (p.slab) render_fwd_kernel<true><<<grid, 256, 0, stream>>>(p);
-    else        render_fwd_kernel<false><<<grid, 256, 0, stream>>>(p);
+    render_fwd_kernel<<<grid, 256, kFwdSmemBytes, stream>>>(p);
     SURFEL_CUDA_OK(cudaGetLastError());
     return 0;
 }

@@ -34,9 +34,12 @@ from . import _cabi
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians"]
 
-# Recalled upstream behaviour in the low-pass branch of the render backward that is NOT the
-# derivative of the forward (adds s.x*dL_dz, s.y*dL_dz to dL_dTw.xy).  Off by default; see DESIGN.md.
-LOWPASS_DEPTH_QUIRK = bool(int(os.environ.get("SURFEL_LOWPASS_DEPTH_QUIRK", "0")))
+# Low-pass branch of the render backward.  The published upstream kernel propagates the depth gradient
+# there as dL_dTw += (s.x, s.y, 1) * dL_dz ("Propagate the gradients of depth") although its forward
+# uses depth = Tw.z in that branch; the reference's training consumes exactly these gradients
+# (/root/reference/train.py:90), so that is the DEFAULT.  SURFEL_LOWPASS_EXACT_DERIVATIVE=1 selects
+# the exact derivative of the forward, (0, 0, 1) * dL_dz, instead (opt-in).
+LOWPASS_DEPTH_QUIRK = not bool(int(os.environ.get("SURFEL_LOWPASS_EXACT_DERIVATIVE", "0")))
 
 # Optional host-side trace (profiles/host_trace.py): when switched on, the autograd node appends
 # (tag, perf_counter_ns, thread id) at the points that bound the host's critical sections — between

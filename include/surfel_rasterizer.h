@@ -29,7 +29,10 @@
  *     opaque workspaces (geometry / binning / image state) whose sizes the *_bytes() functions
  *     return; forward fills them, backward reads them, nothing is retained across calls;
  *   - every launch is ordered on the cudaStream_t passed as `stream` (void*); no call synchronises
- *     the device; the library holds no global mutable state besides the last-error string;
+ *     the device; nothing about a CALL is retained.  Process-global state, all of it optional tooling:
+ *     the last-error string (thread-local), the binning-variant switch (surfel_set_variant /
+ *     SURFEL_SORT), the launch counter and the per-stage profiling switch (surfel_profile_*), and
+ *     the per-device "function attribute set" flags of kernels that opt into large shared memory;
  *   - return value: 0 on success, non-zero on failure with surfel_last_error() describing it
  *     (the Python wrapper raises RuntimeError, like upstream's AT_ERROR path).
  */
@@ -68,11 +71,9 @@ typedef struct surfel_settings {
 int surfel_abi_version(void);
 const char* surfel_last_error(void);
 
-/* Selects between alternative implementations of the same stage (all sm_100a; kept for A/B
- * measurement): "sort" = "bucket" (default) | "radix"; "render_fwd" = "warp" (default) |
- * "g8"; "render_bwd" = "classic" (default) | "tma".  Environment defaults: SURFEL_SORT,
- * SURFEL_RENDER_FWD, SURFEL_RENDER_BWD.  Affects workspace sizes: set it before sizing buffers and do
- * not change it between a forward and its backward. */
+/* Selects between the two binning implementations (both sm_100a, bit-identical output):
+ * "sort" = "bucket" (default: tile buckets + per-tile sort) | "radix" (device-wide CUB-free onesweep).
+ * Environment default: SURFEL_SORT.  Process-global; do not change it between a forward and its backward. */
 int surfel_set_variant(const char* name, const char* value);
 /* 1 iff R passed to surfel_forward_render / surfel_backward may be an upper bound ("capacity") of the
  * true instance count, which lets the caller launch stage 2 before it has read R back. */
@@ -84,13 +85,15 @@ size_t surfel_image_bytes(int W, int H);
 size_t surfel_binning_bytes(size_t R, int W, int H);
 
 /* Byte offsets of the sub-arrays inside the workspaces, for tests and debugging.
- *   geom   : out[0]=splat records (P x 96 B), [1]=tiles_touched u32, [2]=offsets u32 (inclusive),
- *            [3]=clamped u8 (bit c = channel c clamped), [4]=counters u32 ([1] = R)
+ *   geom   : out[0]=render records (P x 128 B: adjugate of T about the splat's screen position, opacity,
+ *            normal, rgb, det T, Tw, culling boxes), [1]=tiles_touched u32, [2]=offsets u32 (inclusive),
+ *            [3]=clamped u8 (bit c = channel c clamped), [4]=counters u32 ([1] = R),
+ *            [5]=transform records (P x 48 B: transMat[9], xy[2], view depth)
  *   binning: out[0]=keys_unsorted u64, [1]=vals_unsorted u32, [2]=keys_sorted u64,
  *            [3]=vals_sorted u32 (the per-tile point list), [4]=ranges uint2 per tile
  *            (unsorted and sorted regions coincide when the sort runs an even number of passes)
  *   image  : out[0]=accum f32 (final_T, M1, M2 planes), [1]=n_contrib u32 (last, median planes) */
-int surfel_geom_offsets(int P, size_t* out5);
+int surfel_geom_offsets(int P, size_t* out6);
 int surfel_binning_offsets(size_t R, int W, int H, size_t* out5);
 int surfel_image_offsets(int W, int H, size_t* out2);
 
@@ -134,7 +137,9 @@ int surfel_render_forward(const surfel_settings_t* s, uint32_t R, const void* ge
  *   dL_dmeans2D (P,3) [densification proxy in .xy, SURVEY A.5], dL_dcolors (P,3),
  *   dL_dopacity (P,1), dL_dmeans3D (P,3), dL_dtransMat (P,9), dL_dsh (P,M,3),
  *   dL_dscales (P,2), dL_drotations (P,4).  Optional outputs may be NULL when the matching input
- *   is absent.  lowpass_depth_quirk: see DESIGN.md (default 0). */
+ *   is absent.  lowpass_depth_quirk: 1 = the published upstream kernel's depth gradient in the low-pass
+ *   branch, dL_dTw += (s.x, s.y, 1) * dL_dz (what callers should pass: the reference trains on it);
+ *   0 = the exact derivative of the forward there, (0, 0, 1) * dL_dz.  See DESIGN.md. */
 int surfel_grad_scratch_floats(void);
 int surfel_backward(const surfel_settings_t* s, int P, int M, uint32_t R, const float* means3D,
                     const float* scales, const float* rotations, const float* transMat_precomp,

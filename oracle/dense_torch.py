@@ -132,13 +132,21 @@ def preprocess(means3D, scales, rotations, opacities, shs, viewmatrix, projmatri
                 tiles_touched=torch.where(visible, (x1 - x0) * (y1 - y0), torch.zeros_like(x0)))
 
 
-def rasterize(pre, bg, W, H, pixel_chunk=4096):
-    """A.3 dense blend.  Returns color (3,H,W), others (7,H,W), n_contrib (H,W), final_T (H,W)."""
+def rasterize(pre, bg, W, H, pixel_chunk=4096, upstream_lowpass_depth=False, xy_override=None):
+    """A.3 dense blend.  Returns color (3,H,W), others (7,H,W), n_contrib (H,W), final_T (H,W).
+
+    upstream_lowpass_depth: emulate, through autograd, the depth gradient the published upstream
+      backward applies in the low-pass branch ("Propagate the gradients of depth": dL_dTw += (s.x, s.y, 1)
+      * dL_dz although the forward uses depth = Tw.z there): the VALUE stays Tw.z, the gradient is that of
+      s.x*Tw.x + s.y*Tw.y + Tw.z with s held fixed.
+    xy_override: (P,2) tensor used instead of pre["xy"] for the low-pass distance, e.g. a detached leaf,
+      so that T.grad excludes the low-pass filter's gradient (the raw dL_dtransMat upstream's
+      densification proxy reads on the scales+rotations path, /root/reference/README.md:118)."""
     dt = pre["T"].dtype
     vis = pre["visible"].nonzero().squeeze(1)
     # global front-to-back order: depth bits ascending, ties by splat index (stable)
     order = vis[torch.argsort(pre["depth"][vis].detach(), stable=True)]
-    T9, xy = pre["T"][order], pre["xy"][order]
+    T9, xy = pre["T"][order], (pre["xy"] if xy_override is None else xy_override)[order]
     Tu, Tv, Tw = T9[:, None, 0:3], T9[:, None, 3:6], T9[:, None, 6:9]
     opa, nrm, rgb = pre["opacity"][order], pre["normal"][order], pre["rgb"][order]
     rect = pre["rect"][order]
@@ -171,7 +179,12 @@ def rasterize(pre, bg, W, H, pixel_chunk=4096):
         rho2d = FILTER_INV_SQUARE * (dx * dx + dy * dy)
         use3d = rho3d <= rho2d
         rho = torch.where(use3d, rho3d, rho2d)
-        depth = torch.where(use3d, sx * Tw[..., 0] + sy * Tw[..., 1] + Tw[..., 2], Tw[..., 2].expand_as(sx))
+        depth3d = sx * Tw[..., 0] + sy * Tw[..., 1] + Tw[..., 2]
+        depth_lp = Tw[..., 2].expand_as(sx)
+        if upstream_lowpass_depth:
+            st = sx.detach() * Tw[..., 0] + sy.detach() * Tw[..., 1]
+            depth_lp = depth_lp + (st - st.detach())      # value Tw.z, gradient (s.x, s.y, 1) * dL_dz
+        depth = torch.where(use3d, depth3d, depth_lp)
         ok = ok & (depth >= NEAR_N)
         power = -0.5 * rho
         ok = ok & ~(power > 0)
@@ -214,11 +227,13 @@ def rasterize(pre, bg, W, H, pixel_chunk=4096):
 
 def render(means3D, scales, rotations, opacities, shs, viewmatrix, projmatrix, campos, bg, W, H,
            sh_degree=3, scale_modifier=1.0, transMat_precomp=None, colors_precomp=None,
-           normalize_quat=True, pixel_chunk=4096):
+           normalize_quat=True, pixel_chunk=4096, upstream_lowpass_depth=False, detach_lowpass_center=False):
     pre = preprocess(means3D, scales, rotations, opacities, shs, viewmatrix, projmatrix, campos,
                      W, H, sh_degree, scale_modifier, transMat_precomp, colors_precomp,
                      normalize_quat)
-    color, others, n_contrib, final_T = rasterize(pre, bg, W, H, pixel_chunk)
+    color, others, n_contrib, final_T = rasterize(
+        pre, bg, W, H, pixel_chunk, upstream_lowpass_depth,
+        pre["xy"].detach() if detach_lowpass_center else None)
     return color, others, pre, n_contrib, final_T
 
 

@@ -107,19 +107,20 @@ def bin_sort(pre, W, H, row0=0, row1=None):
     return out
 
 
-def render_fwd(pre, binned, bg, W, H):
-    HW = H * W
+def render_fwd(pre, binned, bg, W, H, f64=False):
+    """A.3.  f64=True evaluates the same algorithm in double on the same float32 inputs (the exact value
+    of the published formula; the yardstick for float32 rounding noise, not a parity target)."""
     out = dict(color=np.zeros((3, H, W), np.float32), others=np.zeros((7, H, W), np.float32),
                accum=np.zeros((3, H, W), np.float32), n_contrib=np.zeros((2, H, W), np.uint32))
-    del HW
-    lib().oracle_render_fwd(W, H, _p(binned["ranges"]), _p(binned["vals_sorted"]), _p(pre["xy"]),
+    fn = lib().oracle_render_fwd_f64 if f64 else lib().oracle_render_fwd
+    fn(W, H, _p(binned["ranges"]), _p(binned["vals_sorted"]), _p(pre["xy"]),
                             _p(pre["transMat"]), _p(pre["normal_opacity"]), _p(pre["rgb"]),
                             _p(_f32(bg)), _p(out["color"]), _p(out["others"]), _p(out["accum"]),
                             _p(out["n_contrib"]))
     return out
 
 
-def render_bwd(pre, binned, img, bg, dL_dcolor, dL_dothers, W, H, lowpass_quirk=False):
+def render_bwd(pre, binned, img, bg, dL_dcolor, dL_dothers, W, H, lowpass_quirk=True):
     P = pre["radii"].shape[0]
     out = dict(dL_dtransMat=np.zeros((P, 9), np.float64), dL_dmean2D=np.zeros((P, 2), np.float64),
                dL_dopacity=np.zeros(P, np.float64), dL_dnormal=np.zeros((P, 3), np.float64),
@@ -173,7 +174,7 @@ def forward(scene, cam, bg, sh_degree=3, scale_modifier=1.0, row0=0, row1=None):
 
 
 def backward(scene, cam, bg, pre, binned, img, dL_dcolor, dL_dothers, sh_degree=3,
-             scale_modifier=1.0, lowpass_quirk=False):
+             scale_modifier=1.0, lowpass_quirk=True):
     W, H = cam["W"], cam["H"]
     rb = render_bwd(pre, binned, img, bg, dL_dcolor, dL_dothers, W, H, lowpass_quirk)
     return preprocess_bwd(scene["means3D"], scene.get("scales"), scene.get("rotations"),

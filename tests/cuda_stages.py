@@ -37,9 +37,11 @@ class CudaPipeline:
     # ---- stage 1 ----
     def preprocess(self):
         lib, P = self.lib, self.P
-        self.radii = torch.empty(P, dtype=torch.int32, device="cuda")
-        self.geom = torch.zeros(lib.surfel_geom_bytes(P), dtype=torch.uint8, device="cuda")
-        self.img = torch.zeros(lib.surfel_image_bytes(self.W, self.H), dtype=torch.uint8, device="cuda")
+        # workspaces are handed over UNINITIALISED by the product (torch.empty): poison them here so that a
+        # kernel reading a byte it did not write first cannot pass
+        self.radii = torch.full((P,), -1, dtype=torch.int32, device="cuda")
+        self.geom = torch.full((lib.surfel_geom_bytes(P),), 0xFF, dtype=torch.uint8, device="cuda")
+        self.img = torch.full((lib.surfel_image_bytes(self.W, self.H),), 0xFF, dtype=torch.uint8, device="cuda")
         host_R = torch.zeros(1, dtype=torch.int32).pin_memory()
         _cabi.check(lib.surfel_forward_preprocess(
             ctypes.byref(self.cs), P, self.M, _p(self.means3D), _p(self.opacities), _p(self.scales),
@@ -48,18 +50,20 @@ class CudaPipeline:
             host_R.data_ptr(), self.stream))
         torch.cuda.synchronize()
         self.R = int(host_R.item()) & 0xFFFFFFFF
-        offs = (ctypes.c_size_t * 5)()
+        offs = (ctypes.c_size_t * 6)()
         lib.surfel_geom_offsets(P, offs)
         g = self.geom.cpu().numpy()
-        rec = g[offs[0]:offs[0] + P * 96].view(np.float32).reshape(P, 24)
+        rec = g[offs[0]:offs[0] + P * 128].view(np.float32).reshape(P, 32)     # render record (common.cuh)
+        tmr = g[offs[5]:offs[5] + P * 48].view(np.float32).reshape(P, 12)      # transform record
         out = dict(
             radii=self.radii.cpu().numpy(),
             tiles_touched=g[offs[1]:offs[1] + 4 * P].view(np.uint32).copy(),
             offsets=g[offs[2]:offs[2] + 4 * P].view(np.uint32).copy(),
             clamped_bits=g[offs[3]:offs[3] + P].copy(),
-            transMat=rec[:, 0:9].copy(), xy=rec[:, 9:11].copy(), opacity=rec[:, 11].copy(),
-            normal=rec[:, 12:15].copy(), depths=rec[:, 15].copy(), rgb=rec[:, 16:19].copy(),
-            bbox=rec[:, 20:24].copy(), R=self.R)
+            transMat=tmr[:, 0:9].copy(), xy=tmr[:, 9:11].copy(), depths=tmr[:, 11].copy(),
+            opacity=rec[:, 11].copy(), normal=rec[:, 12:15].copy(), rgb=rec[:, 16:19].copy(),
+            adjugate=rec[:, [0, 1, 2, 4, 5, 6, 8, 9, 10]].copy(), det=rec[:, 19].copy(),
+            bbox=rec[:, 24:28].copy(), diag=rec[:, 28:32].copy(), R=self.R)
         out["clamped"] = np.stack([(out["clamped_bits"] >> c) & 1 for c in range(3)], 1).astype(np.uint8)
         return out
 
@@ -71,7 +75,7 @@ class CudaPipeline:
 
     def duplicate(self):
         lib = self.lib
-        self.binning = torch.zeros(lib.surfel_binning_bytes(self.R, self.W, self.H), dtype=torch.uint8, device="cuda")
+        self.binning = torch.full((lib.surfel_binning_bytes(self.R, self.W, self.H),), 0xFF, dtype=torch.uint8, device="cuda")
         _cabi.check(lib.surfel_bin_duplicate(ctypes.byref(self.cs), self.P, self.R, self.geom.data_ptr(),
                                              self.radii.data_ptr(), self.binning.data_ptr(), self.stream))
         torch.cuda.synchronize()
@@ -84,7 +88,7 @@ class CudaPipeline:
     def bucket(self):
         """Production binning path (tile buckets + per-tile sort); same outputs as duplicate()+sort()."""
         lib = self.lib
-        self.binning = torch.zeros(lib.surfel_binning_bytes(self.R, self.W, self.H), dtype=torch.uint8, device="cuda")
+        self.binning = torch.full((lib.surfel_binning_bytes(self.R, self.W, self.H),), 0xFF, dtype=torch.uint8, device="cuda")
         _cabi.check(lib.surfel_bin_bucket(ctypes.byref(self.cs), self.P, self.R, self.geom.data_ptr(),
                                           self.radii.data_ptr(), self.binning.data_ptr(),
                                           self.img.data_ptr() if self.fused_count else None, 1, self.stream))
@@ -108,7 +112,9 @@ class CudaPipeline:
 
     def render(self):
         lib, W, H = self.lib, self.W, self.H
-        self.color = torch.zeros(3, H, W, device="cuda"); self.others = torch.zeros(7, H, W, device="cuda")
+        band = self.cs.tile_row_begin != 0 or self.cs.tile_row_end != 0      # a band leaves the other rows untouched
+        fill = 0.0 if band else float("nan")
+        self.color = torch.full((3, H, W), fill, device="cuda"); self.others = torch.full((7, H, W), fill, device="cuda")
         _cabi.check(lib.surfel_render_forward(ctypes.byref(self.cs), self.R, self.geom.data_ptr(),
                                               self.binning.data_ptr(), self.img.data_ptr(),
                                               self.color.data_ptr(), self.others.data_ptr(), self.stream))
@@ -121,7 +127,7 @@ class CudaPipeline:
                     accum=i[offs[0]:offs[0] + 12 * n].view(np.float32).reshape(3, H, W).copy(),
                     n_contrib=i[offs[1]:offs[1] + 8 * n].view(np.uint32).reshape(2, H, W).copy())
 
-    def backward(self, dL_dcolor, dL_dothers, lowpass_quirk=False):
+    def backward(self, dL_dcolor, dL_dothers, lowpass_quirk=True):
         lib, P, M = self.lib, self.P, self.M
         gc, go = _t(dL_dcolor), _t(dL_dothers)
         e = lambda *s: torch.full(s, float("nan"), device="cuda")

@@ -133,7 +133,8 @@ def main():
     bg = np.zeros(3, np.float32)
     pre, binned, img = O.forward(scn, cmn, bg)
     gc, go = S.make_cotangents(cm["W"], cm["H"], S.CONFIG_SEED["config1"])
-    grads = O.backward(scn, cmn, bg, pre, binned, img, gc.numpy(), go.numpy())
+    grads = O.backward(scn, cmn, bg, pre, binned, img, gc.numpy(), go.numpy())                           # upstream low-pass depth gradient (default)
+    grads_x = O.backward(scn, cmn, bg, pre, binned, img, gc.numpy(), go.numpy(), lowpass_quirk=False)     # exact derivative (opt-in)
     sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
     np.savez_compressed(
         os.path.join(HERE, "oracle_config1.npz"),
@@ -141,7 +142,9 @@ def main():
         sha_vals=sha(binned["vals_sorted"]), sha_ranges=sha(binned["ranges"]), R=binned["R"],
         color=img["color"].astype(np.float16), others=img["others"].astype(np.float32)[:, ::4, ::4],
         n_contrib_sum=np.int64(img["n_contrib"][0].astype(np.int64).sum()),
-        dL_dmeans3D=grads["dL_dmeans3D"], dL_dopacity=grads["dL_dopacity"], dL_dscales=grads["dL_dscales"])
+        dL_dmeans3D=grads["dL_dmeans3D"], dL_dopacity=grads["dL_dopacity"], dL_dscales=grads["dL_dscales"],
+        dL_dmeans2D=grads["dL_dmeans2D"],
+        exact_dL_dmeans3D=grads_x["dL_dmeans3D"], exact_dL_dscales=grads_x["dL_dscales"])
     print("wrote oracle_config1.npz: R", binned["R"])
 
 

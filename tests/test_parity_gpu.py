@@ -37,12 +37,36 @@ def run_both(oracle, scene, cam, bg, sh_degree=3, scale_modifier=1.0, tile_rows=
     return pre, binned, img, pipe
 
 
+def record_stats(name, err, extra=None):
+    """Print and log (gpurun_out/parity_stats.jsonl) the error distribution of one tensor: the worst
+    offender, the 99.9th and 99th percentiles and the median — what the tolerances below are cut to."""
+    import json, os
+    err = np.asarray(err, np.float64).ravel()
+    fin = err[np.isfinite(err)]
+    st = dict(name=name, n=int(err.size), nonfinite=int(err.size - fin.size),
+              max=float(fin.max()) if fin.size else 0.0,
+              p999=float(np.quantile(fin, 0.999)) if fin.size else 0.0,
+              p99=float(np.quantile(fin, 0.99)) if fin.size else 0.0,
+              p50=float(np.quantile(fin, 0.5)) if fin.size else 0.0)
+    st.update(extra or {})
+    st["test"] = os.environ.get("PYTEST_CURRENT_TEST", "").split(" ")[0]
+    print(f"{name}: max {st['max']:.3e}  p99.9 {st['p999']:.3e}  p99 {st['p99']:.3e}  median {st['p50']:.3e}  (n={st['n']})")
+    try:
+        out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_stats.jsonl"), "a") as f:
+            f.write(json.dumps(st) + "\n")
+    except OSError:
+        pass
+    return st
+
+
 def assert_close_budget(name, got, ref, tol=1e-4, budget=FLIP_BUDGET):
     got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
     err = np.abs(got - ref) / np.maximum(1.0, np.abs(ref))
     bad = (err > tol) | ~np.isfinite(got)
     frac = bad.mean()
-    print(f"{name}: max rel err {np.nanmax(err):.3e}, outside {tol:g}: {bad.sum()} of {bad.size} ({frac:.2e})")
+    record_stats(name, err, dict(tol=tol, outside=int(bad.sum()), frac_outside=float(frac), budget=budget))
     assert frac <= budget, f"{name}: {frac:.3e} of entries outside {tol} (budget {budget})"
     return frac
 
@@ -74,6 +98,15 @@ def test_preprocess_and_binning_bitexact(oracle, cuda_lib, case, sh_degree):
     np.testing.assert_array_equal(got["opacity"][vis], pre["normal_opacity"][vis, 3])
     np.testing.assert_allclose(got["rgb"][vis], pre["rgb"][vis], atol=1e-6, rtol=0)
     np.testing.assert_array_equal(got["clamped"][vis], pre["clamped"][vis])
+    # render record: the adjugate of T about the splat's screen position, against float64 numpy
+    T = pre["transMat"][vis].astype(np.float64)
+    c = pre["xy"][vis].astype(np.float64)
+    Tu, Tv, Tw = T[:, 0:3] - c[:, 0:1] * T[:, 6:9], T[:, 3:6] - c[:, 1:2] * T[:, 6:9], T[:, 6:9]
+    adj = np.concatenate([np.cross(Tv, Tw), np.cross(Tw, Tu), np.cross(Tu, Tv)], 1)
+    sc = np.abs(adj).max(1, keepdims=True)
+    assert (np.abs(got["adjugate"][vis] - adj) <= 2e-7 * sc).all()
+    det = (Tu * np.cross(Tv, Tw)).sum(1)
+    assert (np.abs(got["det"][vis] - det) <= 2e-7 * np.abs(det) + 1e-30).all()
     dup = pipe.duplicate()
     np.testing.assert_array_equal(dup["keys_unsorted"], binned["keys_unsorted"])
     np.testing.assert_array_equal(dup["vals_unsorted"], binned["vals_unsorted"])
@@ -151,7 +184,7 @@ def grad_check(name, got, ref, rtol=2e-3, budget=5e-3):
     scale = np.abs(ref).max() + 1e-30
     err = np.abs(got - ref) / (np.abs(ref) + 1e-3 * scale)
     bad = (err > rtol) | ~np.isfinite(got)
-    print(f"{name}: max scaled err {np.nanmax(err):.3e}; outside {rtol:g}: {bad.sum()} of {bad.size}; ref max {scale:.3e}")
+    record_stats(name, err, dict(tol=rtol, outside=int(bad.sum()), frac_outside=float(bad.mean()), budget=budget, ref_max=float(scale)))
     assert bad.mean() <= budget, f"{name}: {bad.mean():.3e} outside tolerance"
 
 
@@ -425,10 +458,10 @@ def test_scale_modifier_and_odd_sizes(oracle, cuda_lib):
     assert_close_budget("allmap", gi["others"], img["others"])
 
 
-@pytest.mark.parametrize("variant", [("sort", "radix", "bucket"), ("render_fwd", "g8", "warp"), ("render_bwd", "tma", "classic")])
+@pytest.mark.parametrize("variant", [("sort", "radix", "bucket")])
 def test_alternative_kernel_variants(oracle, cuda_lib, variant):
-    """The selectable alternatives (device-wide radix sort, 8-lane-group forward, TMA/mbarrier backward)
-    must meet the same parity bar as the defaults, end to end through the public API."""
+    """The selectable alternative (device-wide CUB-free radix sort instead of the tile-bucketed binning)
+    must meet the same parity bar as the default, end to end through the public API."""
     from diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
     name, alt, default = variant
     case = CASES[0]
@@ -460,3 +493,40 @@ def test_alternative_kernel_variants(oracle, cuda_lib, variant):
     grad_check("means3D.grad", leaf["means3D"].grad.cpu().numpy(), ref["dL_dmeans3D"], budget=1e-2)
     grad_check("shs.grad", leaf["shs"].grad.cpu().numpy(), ref["dL_dshs"], budget=1e-2)
     grad_check("opacity.grad", leaf["opacities"].grad.cpu().numpy(), ref["dL_dopacity"], budget=1e-2)
+
+
+@pytest.mark.parametrize("quirk", [True, False])
+@pytest.mark.parametrize("precomp", [False, True])
+def test_lowpass_depth_gradient_and_densification_proxy(oracle, cuda_lib, quirk, precomp):
+    """Both settings of the low-pass depth gradient (True = the published upstream kernel, the default;
+    False = exact derivative) on a scene dominated by low-pass splats (thin, sub-pixel), through the C
+    ABI, against the oracle; and upstream's densification proxy rule: raw dL_dtransMat[2|5] on the
+    scales+rotations path, folded with the low-pass centre gradient on the transMat_precomp path."""
+    case = dict(P=4000, W=200, H=160, seed=21, rotated=True, depth_complexity=25, sigma_scale=0.35)
+    scene, cam = world_scene(**case)
+    bg = np.array([0.2, 0.1, 0.3], np.float32)
+    if precomp:
+        pre0 = oracle.preprocess_fwd(scene["means3D"], scene["scales"], scene["rotations"], scene["opacities"],
+                                     scene["shs"], cam["viewmatrix"], cam["projmatrix"], cam["campos"], cam["W"], cam["H"])
+        T = pre0["transMat"].copy()
+        T[pre0["radii"] == 0] = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1], np.float32)
+        scene = dict(means3D=scene["means3D"], opacities=scene["opacities"], transMat_precomp=T,
+                     colors_precomp=np.clip(pre0["rgb"], 0, 1).astype(np.float32))
+    pre, binned, img, pipe = run_both(oracle, scene, cam, bg)
+    pipe.preprocess(); pipe.bucket(); gi = pipe.render()
+    gc, go = S.make_cotangents(cam["W"], cam["H"], 21)
+    img_gpu = dict(accum=gi["accum"], n_contrib=gi["n_contrib"])
+    ref = oracle.backward(scene, cam, bg, pre, binned, img_gpu, gc.numpy(), go.numpy(), lowpass_quirk=quirk)
+    other = oracle.backward(scene, cam, bg, pre, binned, img_gpu, gc.numpy(), go.numpy(), lowpass_quirk=not quirk)
+    got = pipe.backward(gc.numpy(), go.numpy(), lowpass_quirk=quirk)
+    keys = ("dL_dtransMat", "dL_dcolors", "dL_dopacity", "dL_dmeans2D") if precomp else \
+           ("dL_dmeans3D", "dL_dscales", "dL_drotations", "dL_dopacity", "dL_dshs", "dL_dmeans2D")
+    for k in keys:
+        grad_check(f"{k} (quirk={quirk})", got[k], ref[k])
+    # the scene must separate the two settings, or the test proves nothing
+    # (dL_dTw.xy reaches the scales / rotations; dL_dmeans3D only sees the .z components of dL_dT)
+    k = "dL_dtransMat" if precomp else "dL_dscales"
+    sep = np.abs(ref[k] - other[k]).max() / np.abs(ref[k]).max()
+    assert sep > 1e-2, f"settings differ by only {sep:.2e} on this scene"
+    err_other = np.abs(got[k] - other[k]).max() / np.abs(ref[k]).max()
+    assert err_other > 1e-3, "the CUDA backward ignores the lowpass_depth_quirk argument"
