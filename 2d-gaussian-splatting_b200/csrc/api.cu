@@ -225,6 +225,8 @@ int surfel_render_forward(const surfel_settings_t* s, uint32_t R, const void* ge
     p.rec = (const float4*)((const char*)geom_ws + 0);   // records sit at offset 0 of the geometry workspace
     p.bg = s->bg;
     p.out_color = out_color; p.out_others = out_others;
+    p.out_plane = s->out_plane_stride > 0 ? (size_t)s->out_plane_stride : (size_t)f.W * f.H;
+    if (p.out_plane < (size_t)f.W * f.H) { surfel_set_error("out_plane_stride smaller than the image"); return 1; }
     p.accum = (float*)((char*)image_ws + I.accum); p.n_contrib = (uint32_t*)((char*)image_ws + I.n_contrib);
     return launch_render_fwd(p, (cudaStream_t)stream);
 }
@@ -286,6 +288,8 @@ int surfel_backward(const surfel_settings_t* s, int P, int M, uint32_t R, const 
         p.ranges = v.ranges; p.point_list = v.v_sorted; p.rec = (const float4*)(g + L.rec); p.bg = s->bg;
         p.accum = (float*)((char*)image_ws + I.accum); p.n_contrib = (uint32_t*)((char*)image_ws + I.n_contrib);
         p.dL_dpix = dL_dout_color; p.dL_dothers = dL_dout_others; p.grad_rec = grad_scratch;
+        p.grad_plane = s->grad_plane_stride > 0 ? (size_t)s->grad_plane_stride : (size_t)f.W * f.H;
+        if (p.grad_plane < (size_t)f.W * f.H) { surfel_set_error("grad_plane_stride smaller than the image"); return 1; }
         p.lowpass_quirk = lowpass_depth_quirk;
         if (launch_render_bwd(p, st)) return 1;
     }

@@ -44,6 +44,7 @@ struct RenderParams {
     float* out_color; float* out_others; float* accum; uint32_t* n_contrib;
     // backward
     const float* dL_dpix; const float* dL_dothers; float* grad_rec; int lowpass_quirk;
+    size_t out_plane, grad_plane;   // floats between planes of the outputs / of the cotangents (default H*W)
 };
 
 int launch_preprocess_fwd(const PreFwdParams& p, cudaStream_t stream);

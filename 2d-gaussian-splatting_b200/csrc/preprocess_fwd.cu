@@ -331,17 +331,27 @@ __global__ void __launch_bounds__(kPreBlock, 8) preprocess_fwd_kernel(PreFwdPara
             // screen position c = (cx, cy), in double: in absolute pixel coordinates the adjugate and
             // the conic extents subtract float32 terms of order |pixel|^2 (at 4K the loss
             // exceeded the culling margin). ----
-            const double Twx = tm[6], Twy = tm[7], Twz = tm[8];
-            const double Tux = (double)tm[0] - (double)cx * Twx, Tuy = (double)tm[1] - (double)cx * Twy, Tuz = (double)tm[2] - (double)cx * Twz;
-            const double Tvx = (double)tm[3] - (double)cy * Twx, Tvy = (double)tm[4] - (double)cy * Twy, Tvz = (double)tm[5] - (double)cy * Twz;
-            // P1 = Tv' x Tw, P2 = Tw x Tu', Pc = Tu' x Tv'
-            const double P1x = Tvy * Twz - Tvz * Twy, P1y = Tvz * Twx - Tvx * Twz, P1z = Tvx * Twy - Tvy * Twx;
-            const double P2x = Twy * Tuz - Twz * Tuy, P2y = Twz * Tux - Twx * Tuz, P2z = Twx * Tuy - Twy * Tux;
-            const double Pcx = Tuy * Tvz - Tuz * Tvy, Pcy = Tuz * Tvx - Tux * Tvz, Pcz = Tux * Tvy - Tuy * Tvx;
-            const double det = Tux * P1x + Tuy * P1y + Tuz * P1z;      // det T (invariant under the shift)
+            // records go to the warp's shared-memory panel (11-quad stride: conflict-free) as soon as their
+            // values exist, so that the double-precision temporaries die early
+            float4* r = s_sh + warp * 32 * kShRowQuads + lane * 11;
+            float tu[3], tv[3];          // rows of T about c, rounded once
+            {
+                const double Twx = tm[6], Twy = tm[7], Twz = tm[8];
+                const double Tux = (double)tm[0] - (double)cx * Twx, Tuy = (double)tm[1] - (double)cx * Twy, Tuz = (double)tm[2] - (double)cx * Twz;
+                const double Tvx = (double)tm[3] - (double)cy * Twx, Tvy = (double)tm[4] - (double)cy * Twy, Tvz = (double)tm[5] - (double)cy * Twz;
+                // P1 = Tv' x Tw, P2 = Tw x Tu', Pc = Tu' x Tv', det T = Tu' . P1 (invariant under the shift)
+                const double P1x = Tvy * Twz - Tvz * Twy, P1y = Tvz * Twx - Tvx * Twz, P1z = Tvx * Twy - Tvy * Twx;
+                r[0] = make_float4((float)P1x, (float)P1y, (float)P1z, cx);
+                r[4] = make_float4(rgb[0], rgb[1], rgb[2], (float)(Tux * P1x + Tuy * P1y + Tuz * P1z));
+                r[1] = make_float4((float)(Twy * Tuz - Twz * Tuy), (float)(Twz * Tux - Twx * Tuz), (float)(Twx * Tuy - Twy * Tux), cy);
+                r[2] = make_float4((float)(Tuy * Tvz - Tuz * Tvy), (float)(Tuz * Tvx - Tux * Tvz), (float)(Tux * Tvy - Tuy * Tvx), opa);
+                tu[0] = (float)Tux; tu[1] = (float)Tuy; tu[2] = (float)Tuz;
+                tv[0] = (float)Tvx; tv[1] = (float)Tvy; tv[2] = (float)Tvz;
+            }
 
             // conservative region of {alpha >= 1/255} = low-pass disk  U  projected ellipse rho3d <= tau,
-            // as extents along x, y, x+y and x-y relative to c (render culling)
+            // as extents along x, y, x+y and x-y relative to c (render culling); float32 is
+            // enough here: the rows are already centred
             float ext[8];     // lo/hi along x, y, u = x+y, v = x-y
             const float a255 = 255.0f * opa;
             if (a255 < 0.999f) {
@@ -352,23 +362,23 @@ __global__ void __launch_bounds__(kPreBlock, 8) preprocess_fwd_kernel(PreFwdPara
                 const float r2 = sqrtf(0.5f * tau) + 0.05f;
                 const float r2d = r2 * 1.41421366f;
                 ext[0] = -r2; ext[1] = r2; ext[2] = -r2; ext[3] = r2; ext[4] = -r2d; ext[5] = r2d; ext[6] = -r2d; ext[7] = r2d;
-                const double wxy = Twx * Twx + Twy * Twy, wz2 = Twz * Twz;
-                bool bounded = tm[8] > 0.0f && wz2 > 1.05 * (double)tau * wxy;
+                const float wxy = tm[6] * tm[6] + tm[7] * tm[7], wz2 = tm[8] * tm[8];
+                bool bounded = tm[8] > 0.0f && wz2 > 1.05f * tau * wxy;
                 if (bounded) {
-                    const double d = (double)tau * wxy - wz2;
-                    const double f0 = (double)tau / d, f2 = -1.0 / d;
+                    const float d = tau * wxy - wz2;
+                    const float f0 = tau / d, f2 = -1.0f / d;
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
                         // direction n: T_n = n.x Tu' + n.y Tv'
-                        const double nx = 1.0 - (k == 1), ny = (k == 0) ? 0.0 : (k == 3 ? -1.0 : 1.0);
-                        const double ax = nx * Tux + ny * Tvx, ay = nx * Tuy + ny * Tvy, az = nx * Tuz + ny * Tvz;
-                        const double ec = f0 * (ax * Twx + ay * Twy) + f2 * (az * Twz);
-                        const double ee = f0 * (ax * ax + ay * ay) + f2 * (az * az);
-                        const double eh = sqrt(fmax(0.0, ec * ec - ee));
-                        const double mg = 0.05 + 1e-5 * (fabs(ec) + eh);
+                        const float nx = k == 1 ? 0.0f : 1.0f, ny = k == 0 ? 0.0f : (k == 3 ? -1.0f : 1.0f);
+                        const float ax = nx * tu[0] + ny * tv[0], ay = nx * tu[1] + ny * tv[1], az = nx * tu[2] + ny * tv[2];
+                        const float ec = f0 * (ax * tm[6] + ay * tm[7]) + f2 * (az * tm[8]);
+                        const float ee = f0 * (ax * ax + ay * ay) + f2 * (az * az);
+                        const float eh = sqrtf(fmaxf(0.0f, ec * ec - ee));
+                        const float mg = 0.05f + 1e-4f * (fabsf(ec) + eh);
                         if (!(ec == ec) || !(eh == eh)) bounded = false;
-                        ext[2 * k] = fminf(ext[2 * k], (float)(ec - eh - mg));
-                        ext[2 * k + 1] = fmaxf(ext[2 * k + 1], (float)(ec + eh + mg));
+                        ext[2 * k] = fminf(ext[2 * k], ec - eh - mg);
+                        ext[2 * k + 1] = fmaxf(ext[2 * k + 1], ec + eh + mg);
                     }
                 }
                 if (!bounded) {
@@ -377,15 +387,9 @@ __global__ void __launch_bounds__(kPreBlock, 8) preprocess_fwd_kernel(PreFwdPara
                 }
             }
             const float cu = cx + cy, cv = cx - cy;
-            // records -> the warp's shared-memory panel (11-quad stride: conflict-free); the warp then
-            // streams its 32 render records (4 KB contiguous) and 32 transform records (1.5 KB) to HBM
-            // with fully coalesced 128-bit stores
-            float4* r = s_sh + warp * 32 * kShRowQuads + lane * 11;
-            r[0] = make_float4((float)P1x, (float)P1y, (float)P1z, cx);
-            r[1] = make_float4((float)P2x, (float)P2y, (float)P2z, cy);
-            r[2] = make_float4((float)Pcx, (float)Pcy, (float)Pcz, opa);
+            // the warp then streams its 32 render records (4 KB contiguous) and 32 transform records
+            // (1.5 KB) to HBM with fully coalesced 128-bit stores
             r[3] = make_float4(nrm[0], nrm[1], nrm[2], tm[8]);
-            r[4] = make_float4(rgb[0], rgb[1], rgb[2], (float)det);
             r[5] = make_float4(tm[6], tm[7], __uint_as_float((uint32_t)idx), pvz);
             r[6] = make_float4(cx + ext[0], cy + ext[2], cx + ext[1], cy + ext[3]);
             r[7] = make_float4(cu + ext[4], cu + ext[5], cv + ext[6], cv + ext[7]);

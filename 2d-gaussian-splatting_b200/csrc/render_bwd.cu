@@ -29,6 +29,9 @@ namespace surfel {
 #ifndef SURFEL_BWD_BLOCKS
 #define SURFEL_BWD_BLOCKS 4
 #endif
+#ifndef SURFEL_BWD_SUM
+#define SURFEL_BWD_SUM 2        // column sums: 0 = indexed-branch ladder, 1 = plain loop, 2 = blocks of four
+#endif
 #ifndef SURFEL_BWD_BATCH
 #define SURFEL_BWD_BATCH 352
 #endif
@@ -45,9 +48,24 @@ constexpr int kBwdSmemBytes = kRecBytesB + kBatchB * 4 + kPanelBytes + 8 * kGrou
 static_assert(kPanelRow * 4 == 96, "the ladder below hard-codes the 96-byte row stride");
 __device__ __forceinline__ float column_sum(uint32_t a, int cnt) {
     float acc = 0.0f;
-#ifdef SURFEL_BWD_LOOP_SUM
+#if SURFEL_BWD_SUM == 1
+#pragma unroll 1
     for (int r = 0; r < cnt; r++) acc += lds32(a + r * kPanelRow * 4);
     return acc;
+#elif SURFEL_BWD_SUM == 2
+    // blocks of four rows (independent loads in flight, two partial sums), then the 0-3 leftover rows;
+    // the loops are kept rolled: unrolled by the compiler they turn into a tree of trip-count tests that
+    // costs more than the rows themselves at ~9 rows
+    float acc2 = 0.0f;
+    int r = cnt;
+#pragma unroll 1
+    for (; r >= 4; r -= 4, a += 4 * kPanelRow * 4) {
+        const float x0 = lds32(a), x1 = lds32(a + kPanelRow * 4), x2 = lds32(a + 2 * kPanelRow * 4), x3 = lds32(a + 3 * kPanelRow * 4);
+        acc += x0 + x1; acc2 += x2 + x3;
+    }
+#pragma unroll 1
+    for (; r > 0; r--, a += kPanelRow * 4) acc += lds32(a);
+    return acc + acc2;
 #endif
     asm volatile(
         "{\n"
@@ -123,17 +141,19 @@ __global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(Rend
     if (inside) {
         T_final = p.accum[pix]; final_D = p.accum[HW + pix]; final_D2 = p.accum[2 * HW + pix];
         last_contributor = p.n_contrib[pix]; median_contributor = p.n_contrib[HW + pix];
-        dpix0 = p.dL_dpix[pix]; dpix1 = p.dL_dpix[HW + pix]; dpix2 = p.dL_dpix[2 * HW + pix];
-        dL_ddepth = p.dL_dothers[kChDepth * HW + pix];
-        dL_daccum = p.dL_dothers[kChAlpha * HW + pix];
-        dN0 = p.dL_dothers[(kChNormal + 0) * HW + pix];
-        dN1 = p.dL_dothers[(kChNormal + 1) * HW + pix];
-        dN2 = p.dL_dothers[(kChNormal + 2) * HW + pix];
-        dL_dmedian = p.dL_dothers[kChMidDepth * HW + pix];
-        dL_dreg = p.dL_dothers[kChDistortion * HW + pix];
+        const size_t GP = p.grad_plane;
+        dpix0 = p.dL_dpix[pix]; dpix1 = p.dL_dpix[GP + pix]; dpix2 = p.dL_dpix[2 * GP + pix];
+        dL_ddepth = p.dL_dothers[kChDepth * GP + pix];
+        dL_daccum = p.dL_dothers[kChAlpha * GP + pix];
+        dN0 = p.dL_dothers[(kChNormal + 0) * GP + pix];
+        dN1 = p.dL_dothers[(kChNormal + 1) * GP + pix];
+        dN2 = p.dL_dothers[(kChNormal + 2) * GP + pix];
+        dL_dmedian = p.dL_dothers[kChMidDepth * GP + pix];
+        dL_dreg = p.dL_dothers[kChDistortion * GP + pix];
     }
-    const float final_A = 1.0f - T_final;
-    const float bgT = -T_final * ((__ldg(p.bg + 0) * dpix0 + __ldg(p.bg + 1) * dpix1) + __ldg(p.bg + 2) * dpix2);
+    // distortion terms folded with the pixel's cotangent once: dL/dw_j = D2r + m_j (m_j Ar - 2 D1r),
+    // dL/dm_j = w_j (2 m_j Ar - 2 D1r)   (A = 1 - T_final, D1 = M1, D2 = M2 of the forward)
+    const float Ar = (1.0f - T_final) * dL_dreg, Ar2 = Ar + Ar, nD1r2 = -2.0f * final_D * dL_dreg, D2r = final_D2 * dL_dreg;
     const uint32_t median_index = median_contributor - 1u;   // 0xFFFFFFFE when there is none
     const bool quirk = p.lowpass_quirk != 0;
 
@@ -151,8 +171,11 @@ __global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(Rend
     // with the per-pair scalar "value"
     //     v_j = rgb_j.dL_dC + depth_j*dL_dD + dL_dA + n_j.dL_dN + dL_dweight_j      (dL/dw_j)
     // the A.4 suffix recurrences (accum_rec for colour, depth, alpha, normal and last_dL_dT) collapse
-    // into ONE accumulator S = sum_{j>i} w_j v_j:   dL/dalpha_i = T_i v_i - S/(1-alpha_i) + bg term.
-    float T = T_final, S = 0.0f;
+    // into ONE accumulator S = sum_{j>i} w_j v_j (+ the background term):
+    //     dL/dalpha_i = T_i v_i - S/(1-alpha_i).
+    // S carries the background term as well: S = sum_{j>i} w_j v_j + T_final * bg . dL_dC
+    float T = T_final;
+    float S = T_final * ((__ldg(p.bg + 0) * dpix0 + __ldg(p.bg + 1) * dpix1) + __ldg(p.bg + 2) * dpix2);
     constexpr float kMScale = kFar / (kFar - kNear);
     constexpr float kDmScale = (kFar * kNear) / (kFar - kNear);
 
@@ -206,66 +229,71 @@ __global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(Rend
                 const uint32_t ra = gb + j * 16u;
                 const float4 q0 = lds128(ra), q1 = lds128(ra + kBatchB * 16), q2 = lds128(ra + 2 * kBatchB * 16);
                 PairEval e;
-                bool active = eval_pair(pxf, pyf, q0, q1, q2, e) && (int)j < own;
-                float4 q3, q4;
-                float depth = 0.0f;
-                const bool use3d = e.rho3d <= e.rho2d;
-                if (active) {
-                    q3 = lds128(ra + 3 * kBatchB * 16); q4 = lds128(ra + 4 * kBatchB * 16);
-                    depth = use3d ? q4.w * e.inv_pz : q3.w;      // det T / p.z, or Tw.z in the low-pass branch
-                    active = !(depth < kNear);
-                }
+                const bool active = eval_pair(pxf, pyf, q0, q1, q2, e) && (int)j < own;
                 const unsigned am = __ballot_sync(0xffffffffu, active);
                 if (am == 0u) continue;
 
                 if (active) {
-                    const float G = e.G, alpha = e.alpha;
-                    const float one_m = 1.0f - alpha;
-                    const float inv1ma = fast_rcp(one_m);
-                    T = T * inv1ma;
-                    const float w = alpha * T;
-                    const float inv_d = fast_rcp(depth);
-                    const float m_d = kMScale * (1.0f - kNear * inv_d);
-                    const float dmd_dd = kDmScale * inv_d * inv_d;
-                    const float dL_dweight = (final_D2 + m_d * m_d * final_A - 2.0f * m_d * final_D) * dL_dreg;
-                    float v = dL_dweight + dL_daccum;
-                    v = fmaf(q4.x, dpix0, v); v = fmaf(q4.y, dpix1, v); v = fmaf(q4.z, dpix2, v);
-                    v = fmaf(depth, dL_ddepth, v);
-                    v = fmaf(q3.x, dN0, v); v = fmaf(q3.y, dN1, v); v = fmaf(q3.z, dN2, v);
-                    const float dL_dalpha = T * v - (S - bgT) * inv1ma;
-                    S = fmaf(w, v, S);
-                    float dL_dz = ((int)j == med) ? dL_dmedian : 0.0f;
-                    dL_dz += 2.0f * w * (m_d * final_A - final_D) * dL_dreg * dmd_dd;
-                    const float dL_dG = q2.w * dL_dalpha;
-                    dL_dz += w * dL_ddepth;
-                    float ax = 0, ay = 0, az = 0, zd = 0, zx = 0, zy = 0, zz = 0, m2x = 0, m2y = 0;
-                    if (use3d) {
-                        // G = exp(-0.5 |s|^2), s = p.xy / p.z, depth = det T / p.z
-                        const float t = -G * dL_dG * e.inv_pz;
-                        ax = t * e.sx; ay = t * e.sy;
-                        zd = dL_dz * e.inv_pz;                                   // dL/d(det T)
-                        az = -fmaf(ax, e.sx, fmaf(ay, e.sy, zd * depth));        // dL/dp.z
-                    } else {
-                        // upstream: dL_dmean2D += dL_dG * (-G * FilterInvSquare * d), d = c - pixel = -(dx, dy)
-                        const float gg = G * kFilterInvSquare * dL_dG;
-                        m2x = gg * e.dx; m2y = gg * e.dy;
-                        zz = dL_dz;
-                        // upstream "Propagate the gradients of depth" in this branch: dL_dTw += (s.x, s.y, 1) dL_dz
-                        if (quirk) { zx = e.sx * dL_dz; zy = e.sy * dL_dz; }
-                    }
+                    const float4 q3 = lds128(ra + 3 * kBatchB * 16), q4 = lds128(ra + 4 * kBatchB * 16);
+                    const bool use3d = e.rho3d <= e.rho2d;
+                    const float depth = use3d ? q4.w * e.inv_pz : q3.w;      // det T / p.z, or Tw.z in the low-pass branch
                     // one row per contributing lane (rows are compacted: ballot prefix)
                     const uint32_t ro = panel_base + (uint32_t)__popc(am & lt_mask) * (kPanelRow * 4);
-                    sts128(ro, make_float4(ax, ay, az, e.dx * ax));
-                    sts128(ro + 16, make_float4(e.dx * ay, e.dx * az, e.dy * ax, e.dy * ay));
-                    sts128(ro + 32, make_float4(e.dy * az, zd, zx, zy));
-                    sts128(ro + 48, make_float4(zz, m2x, m2y, G * dL_dalpha));
-                    sts128(ro + 64, make_float4(w * dN0, w * dN1, w * dN2, w * dpix0));
-                    sts64(ro + 80, w * dpix1, w * dpix2);
+                    // A.3's `depth < near` skip (rare: splats reaching through the near plane): the pair was not
+                    // blended, so it leaves T and S alone and contributes a row of zeros
+                    if (__builtin_expect(depth < kNear, 0)) {
+                        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        sts128(ro, z4); sts128(ro + 16, z4); sts128(ro + 32, z4); sts128(ro + 48, z4); sts128(ro + 64, z4);
+                        sts64(ro + 80, 0.f, 0.f);
+                    } else {
+                        float ax = 0, ay = 0, az = 0, zd = 0, zx = 0, zy = 0, zz = 0, m2x = 0, m2y = 0;
+                        const float G = e.G, alpha = e.alpha;
+                        const float inv1ma = fast_rcp(1.0f - alpha);
+                        T = T * inv1ma;
+                        const float w = alpha * T;
+                        const float inv_d = fast_rcp(depth);
+                        const float m_d = fmaf(inv_d, -kMScale * kNear, kMScale);
+                        const float dmd_dd = kDmScale * inv_d * inv_d;
+                        float v = fmaf(m_d, fmaf(m_d, Ar, nD1r2), D2r) + dL_daccum;       // dL_dweight + dL_dA
+                        v = fmaf(q4.x, dpix0, v); v = fmaf(q4.y, dpix1, v); v = fmaf(q4.z, dpix2, v);
+                        v = fmaf(depth, dL_ddepth, v);
+                        v = fmaf(q3.x, dN0, v); v = fmaf(q3.y, dN1, v); v = fmaf(q3.z, dN2, v);
+                        const float dL_dalpha = fmaf(T, v, -(S * inv1ma));
+                        S = fmaf(w, v, S);
+                        float dL_dz = ((int)j == med) ? dL_dmedian : 0.0f;
+                        dL_dz = fmaf(w * dmd_dd, fmaf(m_d, Ar2, nD1r2), dL_dz);
+                        const float dL_dG = q2.w * dL_dalpha;
+                        dL_dz = fmaf(w, dL_ddepth, dL_dz);
+                        const float dop = G * dL_dalpha;
+                        if (use3d) {
+                            // G = exp(-0.5 |s|^2), s = p.xy / p.z, depth = det T / p.z
+                            const float t = -G * dL_dG * e.inv_pz;
+                            ax = t * e.sx; ay = t * e.sy;
+                            zd = dL_dz * e.inv_pz;                                   // dL/d(det T)
+                            az = -fmaf(ax, e.sx, fmaf(ay, e.sy, zd * depth));        // dL/dp.z
+                        } else {
+                            // upstream: dL_dmean2D += dL_dG * (-G * FilterInvSquare * d), d = c - pixel = -(dx, dy)
+                            const float gg = G * kFilterInvSquare * dL_dG;
+                            m2x = gg * e.dx; m2y = gg * e.dy;
+                            zz = dL_dz;
+                            // upstream "Propagate the gradients of depth" in this branch: dL_dTw += (s.x, s.y, 1) dL_dz
+                            if (quirk) { zx = e.sx * dL_dz; zy = e.sy * dL_dz; }
+                        }
+                        sts128(ro, make_float4(ax, ay, az, e.dx * ax));
+                        sts128(ro + 16, make_float4(e.dx * ay, e.dx * az, e.dy * ax, e.dy * ay));
+                        sts128(ro + 32, make_float4(e.dy * az, zd, zx, zy));
+                        sts128(ro + 48, make_float4(zz, m2x, m2y, dop));
+                        sts128(ro + 64, make_float4(w * dN0, w * dN1, w * dN2, w * dpix0));
+                        sts64(ro + 80, w * dpix1, w * dpix2);
+                    }
                 }
                 __syncwarp();
-                if (lane < kGradUsed) {
-                    const float acc = column_sum(panel_base + lane * 4, __popc(am));
-                    if (acc != 0.0f) {
+                {
+                    // every lane sums a column (lanes 22..31 read row padding / the head of the next row — inside
+                    // the panel's allocation — and drop the result): the loop runs converged, with a warp-uniform
+                    // trip count
+                    const float acc = column_sum(panel_base + (uint32_t)__popc(lt_mask) * 4u, __popc(am));
+                    if (lane < kGradUsed && acc != 0.0f) {
                         const uint32_t id = lds32u(idb + j * 4u);
                         atomicAdd(p.grad_rec + (size_t)id * kGradFloats + lane, acc);
                     }

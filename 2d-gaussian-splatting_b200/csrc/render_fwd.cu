@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(256, SURFEL_FWD_BLOCKS) render_fwd_kernel(Rend
                         const uint32_t contributor = k32 - hb;   // 1-based list position
                         const float w = e.alpha * T;
                         const float A = 1.0f - T;
-                        const float mm = kMScale * (1.0f - kNear * fast_rcp(depth));
-                        dist += (mm * mm * A + M2 - 2.0f * mm * M1) * w;
+                        const float mm = fmaf(fast_rcp(depth), -kMScale * kNear, kMScale);
+                        dist = fmaf(fmaf(mm, fmaf(mm, A, -(M1 + M1)), M2), w, dist);     // (mm^2 A + M2 - 2 mm M1) w
                         D += depth * w;
                         M1 += mm * w;
                         M2 += mm * mm * w;
@@ -145,16 +145,17 @@ __global__ void __launch_bounds__(256, SURFEL_FWD_BLOCKS) render_fwd_kernel(Rend
         const size_t pix = (size_t)py * p.W + px;
         p.accum[pix] = T; p.accum[HW + pix] = M1; p.accum[2 * HW + pix] = M2;
         p.n_contrib[pix] = last_contributor & 0x7FFFFFFFu; p.n_contrib[HW + pix] = median_contributor;
+        const size_t OP = p.out_plane;
         p.out_color[pix] = C0 + T * __ldg(p.bg + 0);
-        p.out_color[HW + pix] = C1 + T * __ldg(p.bg + 1);
-        p.out_color[2 * HW + pix] = C2 + T * __ldg(p.bg + 2);
-        p.out_others[kChDepth * HW + pix] = D;
-        p.out_others[kChAlpha * HW + pix] = 1.0f - T;
-        p.out_others[(kChNormal + 0) * HW + pix] = N0;
-        p.out_others[(kChNormal + 1) * HW + pix] = N1;
-        p.out_others[(kChNormal + 2) * HW + pix] = N2;
-        p.out_others[kChMidDepth * HW + pix] = median_depth;
-        p.out_others[kChDistortion * HW + pix] = dist;
+        p.out_color[OP + pix] = C1 + T * __ldg(p.bg + 1);
+        p.out_color[2 * OP + pix] = C2 + T * __ldg(p.bg + 2);
+        p.out_others[kChDepth * OP + pix] = D;
+        p.out_others[kChAlpha * OP + pix] = 1.0f - T;
+        p.out_others[(kChNormal + 0) * OP + pix] = N0;
+        p.out_others[(kChNormal + 1) * OP + pix] = N1;
+        p.out_others[(kChNormal + 2) * OP + pix] = N2;
+        p.out_others[kChMidDepth * OP + pix] = median_depth;
+        p.out_others[kChDistortion * OP + pix] = dist;
     }
 }
 

@@ -74,9 +74,12 @@ class GaussianRasterizationSettings(NamedTuple):
     campos: torch.Tensor
     prefiltered: bool
     debug: bool
-    # extension (keyword-only in practice): tile-row band [begin, end) for the multi-GPU tile-band
-    # partition; None = whole frame.
+    # extensions (keyword-only in practice) for the multi-GPU tile-band partition:
+    # tile_rows = [begin, end) tile-row band, None = whole frame; out_buffers = (color, allmap) views to
+    # render INTO — shapes (3,H,W) / (7,H,W), rows contiguous, both with the same plane stride (e.g. slices
+    # of one frame padded to equal bands, which an in-place all-gather then completes).
     tile_rows: Optional[Tuple[int, int]] = None
+    out_buffers: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
 
 
 def _dev_f32(t, name, align=4):
@@ -96,30 +99,32 @@ def _ptr(t):
     return None if t is None or t.numel() == 0 else t.data_ptr()
 
 
-_struct_cache = {}          # id(settings) -> (settings, struct, tensors): tiny LRU, keeps the objects alive
-
-
-def _settings_struct(rs: GaussianRasterizationSettings, keep):
-    """ctypes view of the settings; cached per settings object (the same NamedTuple is used by the
-    forward and the backward of a call, and by every call of a long-lived GaussianRasterizer)."""
-    ent = _struct_cache.get(id(rs))
-    if ent is not None and ent[0] is rs:
-        keep.extend(ent[2])
-        return ent[1]
+def _settings_struct(rs: GaussianRasterizationSettings, keep, out_plane=0, grad_plane=0):
+    """ctypes view of the settings.  Built on every call: the reference's world_view_transform /
+    full_proj_transform are transposed views, so contiguous copies are made here and must see the
+    caller's current values (a long-lived GaussianRasterizer whose camera tensors are updated in place
+    would otherwise render with stale matrices); the four tiny copies cost microseconds."""
     bg = _dev_f32(rs.bg, "bg")
     vm = _dev_f32(rs.viewmatrix, "viewmatrix")
     pm = _dev_f32(rs.projmatrix, "projmatrix")
     cp = _dev_f32(rs.campos, "campos")
     keep.extend([bg, vm, pm, cp])
     rows = rs.tile_rows if len(rs) > 12 and rs.tile_rows is not None else (0, 0)
-    cs = _cabi.SurfelSettings(
+    return _cabi.SurfelSettings(
         int(rs.image_height), int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy),
         float(rs.scale_modifier), int(rs.sh_degree), int(bool(rs.prefiltered)), int(bool(rs.debug)),
-        int(rows[0]), int(rows[1]), bg.data_ptr(), vm.data_ptr(), pm.data_ptr(), cp.data_ptr())
-    if len(_struct_cache) >= 16:
-        _struct_cache.pop(next(iter(_struct_cache)))
-    _struct_cache[id(rs)] = (rs, cs, [bg, vm, pm, cp])
-    return cs
+        int(rows[0]), int(rows[1]), bg.data_ptr(), vm.data_ptr(), pm.data_ptr(), cp.data_ptr(),
+        int(out_plane), int(grad_plane))
+
+
+def _plane_stride(t, C, H, W):
+    """Plane stride (in elements) of a (C,H,W) float32 CUDA tensor whose rows are contiguous, or None."""
+    if t is None or not t.is_cuda or t.dtype != torch.float32 or tuple(t.shape) != (C, H, W):
+        return None
+    st = t.stride()
+    if st[2] != 1 or st[1] != W or st[0] < H * W or t.data_ptr() % 4:
+        return None
+    return st[0]
 
 
 _pinned_counter = {}
@@ -132,7 +137,8 @@ def last_num_rendered():
 
 
 
-_capacity = {}
+_capacity = {}               # (device, P, W, H, band) -> instance capacity seen last; bounded (oldest evicted)
+_CAPACITY_ENTRIES = 64
 # SURFEL_SPECULATIVE=0 restores upstream's launch order (block on R, then launch binning + render)
 _SPECULATIVE = bool(int(os.environ.get("SURFEL_SPECULATIVE", "1")))
 
@@ -144,6 +150,30 @@ def _pinned_u32(device):
         ent = (torch.zeros(1, dtype=torch.int32).pin_memory(), torch.cuda.Event())
         _pinned_counter[key] = ent
     return ent
+
+
+def _grad_buffers(lib, dev, P, M, has_sh, has_colors, has_scales, has_cov):
+    """Every gradient the backward writes, carved out of ONE flat allocation (offsets are multiples of four
+    floats, so the 128-bit stores of the kernels stay aligned): a caller that has to reduce the gradients
+    across ranks (surfel_parallel) reduces `bucket` in place instead of concatenating eight tensors."""
+    parts = [("d_means3D", (P, 3), True), ("d_means2D", (P, 3), True), ("d_opacity", (P, 1), True),
+             ("d_sh", (P, M, 3), has_sh), ("d_scales", (P, 2), has_scales), ("d_rot", (P, 4), has_scales),
+             ("d_colors", (P, 3), has_colors), ("d_cov", (P, 9), has_cov)]
+    off, plan = 0, []
+    for name, shape, on in parts:
+        n = 1
+        for d in shape:
+            n *= d
+        if on:
+            plan.append((name, shape, off, n))
+            off += (n + 3) // 4 * 4
+    bucket = torch.empty((max(off, 4),), dtype=torch.float32, device=dev)
+    out = {name: None for name, _, _ in parts}
+    for name, shape, o, n in plan:
+        out[name] = bucket[o:o + n].view(shape)
+    out["bucket"] = bucket
+    out["scratch"] = torch.empty((max(P, 1), lib.surfel_grad_scratch_floats()), dtype=torch.float32, device=dev)
+    return out
 
 
 class _RasterizeGaussians(torch.autograd.Function):
@@ -161,7 +191,14 @@ class _RasterizeGaussians(torch.autograd.Function):
         dev = means3D.device
         H, W = int(rs.image_height), int(rs.image_width)
         keep = []
-        cs = _settings_struct(rs, keep)
+        outb = rs.out_buffers if len(rs) > 13 else None
+        out_plane = 0
+        if outb is not None:
+            out_plane = _plane_stride(outb[0], 3, H, W)
+            if out_plane is None or _plane_stride(outb[1], 7, H, W) != out_plane or outb[0].device != dev:
+                raise RuntimeError("out_buffers must be float32 CUDA views of shape (3,H,W) and (7,H,W) with "
+                                   "contiguous rows and one common plane stride")
+        cs = _settings_struct(rs, keep, out_plane=out_plane)
         means3D = _dev_f32(means3D, "means3D")
         opacities = _dev_f32(opacities, "opacities")
         sh = _dev_f32(sh, "shs", 16) if sh is not None and sh.numel() else None
@@ -174,8 +211,11 @@ class _RasterizeGaussians(torch.autograd.Function):
         stream = torch.cuda.current_stream(dev).cuda_stream
         band = cs.tile_row_begin != 0 or cs.tile_row_end != 0
         alloc = torch.zeros if band else torch.empty
-        color = alloc((3, H, W), dtype=torch.float32, device=dev)
-        allmap = alloc((7, H, W), dtype=torch.float32, device=dev)
+        if outb is not None:
+            color, allmap = outb            # the caller owns what lies outside the band
+        else:
+            color = alloc((3, H, W), dtype=torch.float32, device=dev)
+            allmap = alloc((7, H, W), dtype=torch.float32, device=dev)
         radii = torch.empty((P,), dtype=torch.int32, device=dev)
         geom = torch.empty((lib.surfel_geom_bytes(P),), dtype=torch.uint8, device=dev)
         img = torch.empty((lib.surfel_image_bytes(W, H),), dtype=torch.uint8, device=dev)
@@ -206,16 +246,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                 # the host blocks: after the wait, the host's critical path to the backward launch (which
                 # must land before the queued forward kernels drain) is as short as possible.
                 if any(ctx.needs_input_grad[:8]):
-                    def e(*shape):
-                        return torch.empty(shape, dtype=torch.float32, device=dev)
-                    ctx.bwd_bufs = dict(
-                        d_means2D=e(P, 3), d_opacity=e(P, 1), d_means3D=e(P, 3),
-                        d_colors=e(P, 3) if colors_precomp is not None else None,
-                        d_cov=e(P, 9) if cov3Ds_precomp is not None else None,
-                        d_sh=e(P, M, 3) if sh is not None else None,
-                        d_scales=e(P, 2) if scales is not None else None,
-                        d_rot=e(P, 4) if scales is not None else None,
-                        scratch=e(max(P, 1), lib.surfel_grad_scratch_floats()))
+                    ctx.bwd_bufs = _grad_buffers(lib, dev, P, M, sh is not None, colors_precomp is not None,
+                                                 scales is not None, cov3Ds_precomp is not None)
                 _mark("speculative_work_launched")
                 ev.synchronize()
                 _mark("R_known")
@@ -223,6 +255,9 @@ class _RasterizeGaussians(torch.autograd.Function):
                 if R > cap or not cap:
                     cap = R if not spec else int(R * 1.25) + 4096
                     if spec:
+                        _capacity.pop(key, None)
+                        while len(_capacity) >= _CAPACITY_ENTRIES:
+                            _capacity.pop(next(iter(_capacity)))
                         _capacity[key] = cap
                     binning = None
             if P == 0 or binning is None:
@@ -237,6 +272,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         ctx.M = M
         ctx.flags = (sh is not None, colors_precomp is not None, scales is not None, cov3Ds_precomp is not None)
         none = torch.empty(0, device=dev)
+        ctx.out_plane = out_plane
         ctx.save_for_backward(means3D, none if scales is None else scales,
                               none if rotations is None else rotations,
                               none if cov3Ds_precomp is None else cov3Ds_precomp,
@@ -256,20 +292,25 @@ class _RasterizeGaussians(torch.autograd.Function):
         dev = means3D.device
         H, W = int(rs.image_height), int(rs.image_width)
         keep = []
-        cs = _settings_struct(rs, keep)
-        g_color = _dev_f32(grad_color if grad_color is not None else torch.zeros((3, H, W), device=dev), "grad_color")
-        g_all = _dev_f32(grad_allmap if grad_allmap is not None else torch.zeros((7, H, W), device=dev), "grad_allmap")
+        if grad_color is None:
+            grad_color = torch.zeros((3, H, W), device=dev)
+        if grad_allmap is None:
+            grad_allmap = torch.zeros((7, H, W), device=dev)
+        # cotangents are read in place when they are plane-strided views with contiguous rows (e.g. slices of a
+        # padded frame); anything else is made contiguous first
+        gp = _plane_stride(grad_color, 3, H, W)
+        if gp is None or _plane_stride(grad_allmap, 7, H, W) != gp:
+            gp = 0
+            g_color, g_all = _dev_f32(grad_color, "grad_color"), _dev_f32(grad_allmap, "grad_allmap")
+        else:
+            g_color, g_all = grad_color, grad_allmap
+        cs = _settings_struct(rs, keep, out_plane=getattr(ctx, "out_plane", 0), grad_plane=gp)
 
-        def e(*shape):
-            return torch.empty(shape, dtype=torch.float32, device=dev)
         b = getattr(ctx, "bwd_bufs", None)
         if b is None:      # P == 0, or backward called twice (retain_graph): allocate here
-            b = dict(d_means2D=e(P, 3), d_opacity=e(P, 1), d_means3D=e(P, 3),
-                     d_colors=e(P, 3) if has_colors else None, d_cov=e(P, 9) if has_cov else None,
-                     d_sh=e(P, M, 3) if has_sh else None, d_scales=e(P, 2) if has_scales else None,
-                     d_rot=e(P, 4) if has_scales else None,
-                     scratch=e(max(P, 1), lib.surfel_grad_scratch_floats()))
+            b = _grad_buffers(lib, dev, P, M, has_sh, has_colors, has_scales, has_cov)
         ctx.bwd_bufs = None
+        ctx.grad_bucket = b["bucket"]
         d_means2D, d_opacity, d_means3D = b["d_means2D"], b["d_opacity"], b["d_means3D"]
         d_colors, d_cov, d_sh, d_scales, d_rot, scratch = b["d_colors"], b["d_cov"], b["d_sh"], b["d_scales"], b["d_rot"], b["scratch"]
         stream = torch.cuda.current_stream(dev).cuda_stream

@@ -22,6 +22,7 @@ class SurfelSettings(ctypes.Structure):
         ("sh_degree", ctypes.c_int32), ("prefiltered", ctypes.c_int32), ("debug", ctypes.c_int32),
         ("tile_row_begin", ctypes.c_int32), ("tile_row_end", ctypes.c_int32),
         ("bg", c_void_p), ("viewmatrix", c_void_p), ("projmatrix", c_void_p), ("campos", c_void_p),
+        ("out_plane_stride", ctypes.c_int64), ("grad_plane_stride", ctypes.c_int64),
     ]
 
 
@@ -101,7 +102,7 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype, fn.argtypes = res, args
-    if lib.surfel_abi_version() != 1:
+    if lib.surfel_abi_version() != 2:
         raise ImportError("libsurfel_b200.so ABI version mismatch")
     _lib = lib
     return lib

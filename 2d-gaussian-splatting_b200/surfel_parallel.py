@@ -8,13 +8,15 @@ BASELINE.json's configs 4 and 5 name.
    is NO collective on the data path.  `allreduce_gradients` is only needed when the ranks train one
    shared model.
 
-2. Tile-band partition of ONE oversized frame (config 5): rank r owns the tile rows
-   [floor(gy*r/n), floor(gy*(r+1)/n)).  Every rank preprocesses all splats but clips each splat's tile
-   rect to its band (C ABI: surfel_settings.tile_row_begin/end), so only its own instances are
-   emitted, sorted and blended; sort keys stay bit-identical to the single-GPU run restricted to the
-   band.  The one exchange step is an all-gather of the band outputs (10 planes); in the backward the
-   per-pixel cotangents are simply sliced (no communication) and the per-splat gradients, which are
-   partial sums over the band's pixels, are summed with one all-reduce.
+2. Tile-band partition of ONE oversized frame (config 5): rank r owns a band of tile rows (equal bands of
+   ceil(gy/n) rows for the copy-free path `rasterize_tile_band`; the floor(gy*r/n) split of SURVEY §8e
+   for the helper functions below, which the CPU tests exercise).  Every rank preprocesses all splats
+   but clips each splat's tile rect to its band (C ABI: surfel_settings.tile_row_begin/end), so only its
+   own instances are emitted, sorted and blended; sort keys stay bit-identical to the single-GPU run
+   restricted to the band.  The one exchange step is an all-gather of the band outputs (10 planes), done
+   IN PLACE in a frame padded to equal bands; in the backward the per-pixel cotangents are read in place
+   (no communication) and the per-splat gradients, which are partial sums over the band's pixels, are
+   summed with one all-reduce of the op's flat gradient bucket.
 
 Collectives go through torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests).
 """
@@ -93,25 +95,105 @@ def allreduce_gradients(grads: Sequence[torch.Tensor], group=None) -> None:
         off += n
 
 
-class _BandGather(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, planes, H, rank, world, group):
-        ctx.meta = (H, rank, world)
-        return gather_band_outputs(planes, H, rank, world, group)
+# ---------------------------------------------------------------------------------------------------
+# Tile-band frame, copy-free exchange.
+#
+# The frame is allocated PADDED to `world` equal bands of ceil(gy / world) tile rows, planar (10, H_pad, W).
+# Every rank renders its band straight into that tensor (the op takes the output views and their plane
+# stride), then ONE in-place all-gather per plane completes it: rank r's chunk of plane c is the contiguous
+# block of rows [r * rows, (r + 1) * rows), i.e. exactly the send buffer NCCL's in-place all-gather expects
+# (sendbuff == recvbuff + rank * count).  No pad / stitch / cat copies; the returned render and allmap are
+# views of the padded tensor.  In the backward the cotangents are read in place (the band kernels only
+# touch their own rows) and the per-splat gradients, which the op writes into one flat bucket, are summed by
+# one in-place all-reduce of that bucket.
+# ---------------------------------------------------------------------------------------------------
+def equal_band_rows(H: int, world: int) -> int:
+    """Tile rows per rank of the equal-band partition (the last ranks may own fewer real rows)."""
+    return (tile_rows(H) + world - 1) // world
+
+
+def equal_band(H: int, rank: int, world: int) -> Tuple[int, int]:
+    gy, rp = tile_rows(H), equal_band_rows(H, world)
+    return min(gy, rank * rp), min(gy, (rank + 1) * rp)
+
+
+def padded_frame(C: int, H: int, W: int, world: int, device, dtype=torch.float32) -> torch.Tensor:
+    return torch.empty((C, equal_band_rows(H, world) * world * TILE, W), device=device, dtype=dtype)
+
+
+def allgather_frame_inplace(buf: torch.Tensor, H: int, rank: int, world: int, group=None) -> None:
+    """Completes a padded frame (C, H_pad, W) in which this rank has written its own band."""
+    if world == 1 or not dist.is_initialized():
+        return
+    C, Hp, W = buf.shape
+    rows = Hp // world
+    for c in range(C):
+        plane = buf[c]
+        send = plane[rank * rows:(rank + 1) * rows].reshape(-1)
+        if not buf.is_cuda:
+            send = send.clone()          # gloo (CPU tests) does not take an aliased send buffer
+        dist.all_gather_into_tensor(plane.reshape(-1), send, group=group)
+
+
+_last = {"grad_bucket": None, "frame": None}
+
+
+def last_exchange_buffers():
+    """(padded frame, flat gradient bucket) of the most recent tile-band step in this process — for
+    measurement code that wants to time the collectives on the real buffers."""
+    return _last["frame"], _last["grad_bucket"]
+
+
+class _BandFrame(torch.autograd.Function):
+    """One oversized frame rendered cooperatively: this rank's band by the CUDA op, the rest by the in-place
+    all-gather.  Wraps the op's own autograd node (same forward / backward code) and adds the exchange."""
 
     @staticmethod
-    def backward(ctx, grad):
-        H, rank, world = ctx.meta
-        return slice_band_cotangent(grad, H, rank, world), None, None, None, None
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                settings, rank, world, group, grad_reduce):
+        from diff_surfel_rasterization import _RasterizeGaussians
+        H, W = int(settings.image_height), int(settings.image_width)
+        buf = padded_frame(10, H, W, world, means3D.device)
+        band = equal_band(H, rank, world)
+        rs = settings._replace(tile_rows=band, out_buffers=(buf[:3, :H], buf[3:, :H]))
+        color, radii, allmap = _RasterizeGaussians.forward(ctx, means3D, means2D, sh, colors_precomp, opacities,
+                                                           scales, rotations, cov3Ds_precomp, rs)
+        allgather_frame_inplace(buf, H, rank, world, group)
+        _last["frame"] = buf
+        if world > 1 and dist.is_initialized():
+            # radii (and so visibility_filter / max_radii2D downstream) are per-band partials: a splat's tile
+            # rect is clipped to the band before it is counted
+            dist.all_reduce(radii, op=dist.ReduceOp.MAX, group=group)
+        ctx.band_meta = (world, group, grad_reduce)
+        return color, radii, allmap
+
+    @staticmethod
+    def backward(ctx, g_color, g_radii, g_allmap):
+        from diff_surfel_rasterization import _RasterizeGaussians
+        world, group, grad_reduce = ctx.band_meta
+        grads = _RasterizeGaussians.backward(ctx, g_color, None, g_allmap)
+        _last["grad_bucket"] = ctx.grad_bucket
+        if grad_reduce == "all_reduce" and world > 1 and dist.is_initialized():
+            dist.all_reduce(ctx.grad_bucket, op=dist.ReduceOp.SUM, group=group)   # every gradient, one collective, in place
+        return grads[:8] + (None, None, None, None, None)
 
 
-def rasterize_tile_band(rasterizer_cls, settings, rank: int, world: int, group=None, **inputs) -> Dict[str, torch.Tensor]:
-    """One oversized frame split over `world` GPUs: render this rank's tile-row band with the CUDA op,
-    then stitch the full frame on every rank with one all-gather.  Differentiable: gradients of the
-    per-splat inputs come back as this band's partial sums (call allreduce_gradients on them)."""
-    H = int(settings.image_height)
-    band = tile_row_band(H, rank, world)
-    rs = settings._replace(tile_rows=band)
-    color, radii, allmap = rasterizer_cls(rs)(**inputs)
-    full = _BandGather.apply(torch.cat([color, allmap], 0), H, rank, world, group)
-    return {"render": full[:3], "allmap": full[3:], "radii": radii, "band": band}
+def rasterize_tile_band(rasterizer_cls, settings, rank: int, world: int, group=None, grad_reduce: str = "all_reduce",
+                        **inputs) -> Dict[str, torch.Tensor]:
+    """One oversized frame split over `world` GPUs (BASELINE config 5).  Returns the COMPLETE
+    frame on every rank ("render" (3,H,W), "allmap" (7,H,W): views of one padded tensor), "radii" reduced
+    with MAX over the ranks, and the band this rank rendered.  Differentiable; with grad_reduce="all_reduce"
+    (default) the gradients that reach the inputs are already summed over the ranks; "none" leaves this
+    band's partial sums (the caller reduces them, e.g. with a reduce-scatter for a sharded optimizer).
+    `rasterizer_cls` is accepted for symmetry with the single-GPU call and is not used."""
+    del rasterizer_cls
+    if grad_reduce not in ("all_reduce", "none"):
+        raise ValueError("grad_reduce must be 'all_reduce' or 'none'")
+    empty = torch.Tensor([])
+    g = lambda k: inputs.get(k) if inputs.get(k) is not None else empty
+    if (inputs.get("shs") is None) == (inputs.get("colors_precomp") is None):
+        raise Exception("Please provide excatly one of either SHs or precomputed colors!")
+    color, radii, allmap = _BandFrame.apply(inputs["means3D"], inputs["means2D"], g("shs"), g("colors_precomp"),
+                                            inputs["opacities"], g("scales"), g("rotations"), g("cov3D_precomp"),
+                                            settings, rank, world, group, grad_reduce)
+    return {"render": color, "allmap": allmap, "radii": radii, "band": equal_band(int(settings.image_height), rank, world)}

@@ -36,6 +36,11 @@ METRIC = "fwd+bwd Msplats/sec at 1M surfels/1080p"
 UNIT = "Msplats/s"
 
 
+def workload_string(name, P, W, H):
+    """config.workload: the same string in both arms."""
+    return f"{name}: {P} surfels, {W}x{H}, SH degree 3, fwd+bwd, one view per GPU"
+
+
 def algorithmic_bytes(P, V, R, W, H):
     """SURVEY §8(d) / BASELINE.md §2.3 per-stage algorithmic bytes."""
     N = W * H
@@ -161,6 +166,7 @@ def cpu_oracle_run(scene_np, cam_np, gc, go, P, max_seconds=25.0):
     import numpy as np
     from oracle import surfel_oracle as O
     O.build()
+    O.set_threads(0)          # every host core, whatever OMP_NUM_THREADS says (torchrun exports 1 into each rank)
     bg = np.zeros(3, np.float32)
     gy = (cam_np["H"] + 15) // 16
     # probe with a thin band to estimate the cost of the full frame
@@ -197,7 +203,13 @@ def run_reference(args, rank, world):
     scene, cam = S.named(args.workload)
     gc, go = S.make_cotangents(W, H, S.CONFIG_SEED[args.workload])
     sn, cn = S.to_numpy(scene), S.to_numpy(cam)
-    cores = os.cpu_count()
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count()))    # a launcher may have pinned the rank to a few cores
+    except Exception:
+        pass
+    from oracle import surfel_oracle as O
+    O.build()
+    cores = O.set_threads(0)
     # CPU steps are seconds long: run at most 6 timed + 1 warm-up sample however large K is, each
     # bounded so that the whole arm ends within a few minutes; the JSON line reports the real counts.
     n_warm, n_steps = min(args.warmup, 1), min(args.steps, 6)
@@ -214,12 +226,92 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: {P} surfels, {W}x{H}, SH degree 3, fwd+bwd"},
+        "config": {"workload": workload_string(args.workload, P, W, H),
+                   "note": "one host serves every view: at N GPUs the repo arm renders N views per step on N devices, this arm is "
+                           "the throughput of the box's host cores on the same per-view workload"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference CUDA rasterizer is not vendored in /root/reference; this is the CPU restatement (oracle/)",
     }
     _emit(json.dumps(out))
+
+
+def tile_band_leg(rank, world, dev, steps=6, warmup=2, workload="config5"):
+    """Second leg at N > 1 (BASELINE config 5): ONE oversized frame rendered in N tile-row bands,
+    the band outputs completed by in-place all-gathers over NVLink, the per-splat gradients summed by one
+    all-reduce of the op's flat gradient bucket.  Device times (CUDA events), max over ranks."""
+    import torch
+    import torch.distributed as dist
+    import surfel_parallel as SP
+    import surfel_scenes as S
+    from diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    P, W, H = S.CONFIGS[workload]
+    scene, cam = S.named(workload)                       # same seed on every rank: replicated splats
+    rs = GaussianRasterizationSettings(
+        image_height=H, image_width=W, tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"], bg=torch.zeros(3, device=dev),
+        scale_modifier=1.0, viewmatrix=cam["viewmatrix"].to(dev), projmatrix=cam["projmatrix"].to(dev), sh_degree=3,
+        campos=cam["campos"].to(dev), prefiltered=False, debug=False)
+    names = ("means3D", "scales", "rotations", "opacities", "shs")
+    leaf = {k: scene[k].to(dev).requires_grad_(True) for k in names}
+    m2d = torch.zeros(P, 3, device=dev, requires_grad=True)
+    gc, go = S.make_cotangents(W, H, 5)
+    gc, go = gc.to(dev), go.to(dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
+    acc = [0.0] * 6
+
+    def step(timed):
+        for t in list(leaf.values()) + [m2d]:
+            t.grad = None
+        ev[0].record()
+        res = SP.rasterize_tile_band(GaussianRasterizer, rs, rank, world, grad_reduce="none", means3D=leaf["means3D"],
+                                     means2D=m2d, shs=leaf["shs"], opacities=leaf["opacities"], scales=leaf["scales"],
+                                     rotations=leaf["rotations"])
+        ev[1].record()                                                       # band forward + in-place all-gathers
+        torch.autograd.backward([res["render"], res["allmap"]], [gc, go])    # cotangents read in place, band backward
+        ev[2].record()
+        frame, bucket = SP.last_exchange_buffers()
+        dist.all_reduce(bucket)                                              # sum of the band partials, one collective
+        ev[3].record()
+        # the collectives once more on the same buffers, alone (the gather is idempotent; the second all-reduce
+        # only scales this step's throw-away gradients), so that their cost can be separated from the kernels'
+        ev[4].record()
+        SP.allgather_frame_inplace(frame, H, rank, world)
+        ev[5].record()
+        shard = torch.empty(bucket.numel() // world, device=dev) if bucket.numel() % world == 0 else None
+        if shard is not None:
+            dist.reduce_scatter_tensor(shard, bucket)
+        ev[6].record()
+        torch.cuda.synchronize()
+        if timed:
+            for i, (a, b) in enumerate(((0, 1), (1, 2), (2, 3), (4, 5), (5, 6), (0, 3))):
+                acc[i] += ev[a].elapsed_time(ev[b])
+        return res
+
+    for _ in range(warmup):
+        res = step(False)
+    dist.barrier(); torch.cuda.synchronize()
+    for _ in range(steps):
+        res = step(True)
+    tt = torch.tensor([a / steps for a in acc], device=dev, dtype=torch.float64)
+    dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    fwd_total, bwd, allreduce, gather, rscatter, frame = (float(x) for x in tt)
+    out = {"workload": f"{workload}: {P} surfels, one {W}x{H} frame in {world} tile-row bands",
+           "ms_frame": frame, "ms_band_fwd": max(0.0, fwd_total - gather), "ms_allgather": gather, "ms_band_bwd": bwd,
+           "ms_allreduce": allreduce, "ms_reduce_scatter_alternative": rscatter,
+           "gather_bytes_per_rank": int(10 * 4 * W * SP.equal_band_rows(H, world) * 16),
+           "grad_bytes": int(SP.last_exchange_buffers()[1].numel() * 4),
+           "Msplats_per_s": P / frame / 1e3, "steps": steps,
+           "how": "padded frame, bands rendered in place, one in-place all_gather_into_tensor per plane; cotangents read in "
+                  "place; one all_reduce of the flat gradient bucket (reduce-scatter timed as the sharded-optimizer alternative)"}
+    if rank == 0:
+        # the completed frame against ONE GPU rendering the whole frame
+        with torch.no_grad():
+            color, radii, allmap = GaussianRasterizer(rs)(means3D=leaf["means3D"], means2D=m2d, shs=leaf["shs"],
+                                                          opacities=leaf["opacities"], scales=leaf["scales"], rotations=leaf["rotations"])
+        out["stitched_equals_single_gpu"] = bool(torch.equal(res["render"], color) and torch.equal(res["allmap"], allmap)
+                                                 and torch.equal(res["radii"], radii))
+    dist.barrier()
+    return out
 
 
 def run_ours(args, rank, local_rank, world):
@@ -422,12 +514,22 @@ def run_ours(args, rank, local_rank, world):
         except Exception as ex:   # never let the optional extra break the bench line
             cpu_baseline["pure_python_config1_forward"] = {"error": str(ex)[:200]}
 
+    # ---- tile-band leg (N > 1): ONE config-5 frame in N bands, exchange over NVLink ----
+    tile_band = None
+    if world > 1 and not args.no_tile_band:
+        try:
+            del leaf, means2D, gc, go
+            torch.cuda.empty_cache()
+            tile_band = tile_band_leg(rank, world, dev)
+        except Exception as ex:      # the headline line must survive a failure of the second leg
+            tile_band = {"error": f"{type(ex).__name__}: {str(ex)[:300]}"}
+
     if rank == 0:
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {P} surfels, {W}x{H}, SH degree 3, fwd+bwd, one view per GPU",
+            "config": {"workload": workload_string(args.workload, P, W, H),
                        "visible": V, "instances": R, "parallelism": f"view-parallel x{world} (no collective)",
                        "host_numa_node": numa_node,
                        "l2_policy": "inputs larger than L2 (232 MB of splat parameters + 83 MB of outputs per step vs 126 MB L2)"},
@@ -436,6 +538,8 @@ def run_ours(args, rank, local_rank, world):
         }
         if cpu_baseline is not None:
             out["cpu_baseline"] = cpu_baseline
+        if tile_band is not None:
+            out["tile_band"] = tile_band
         _emit(json.dumps(out))
 
 
@@ -474,6 +578,7 @@ def main():
     ap.add_argument("--splats", type=int, default=0, help="override P (debugging only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (profiling runs only)")
+    ap.add_argument("--no-tile-band", action="store_true", help="skip the tile-band leg that runs at N > 1")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define SURFEL_ABI_VERSION 1
+#define SURFEL_ABI_VERSION 2
 
 /* Mirrors GaussianRasterizationSettings (fields constructed at
  * /root/reference/gaussian_renderer/__init__.py:37-51) plus the tile-row band used by the
@@ -66,6 +66,12 @@ typedef struct surfel_settings {
     const float* viewmatrix;  /* (4,4)  device, row-vector convention (scene/cameras.py:56) */
     const float* projmatrix;  /* (4,4)  device, viewmatrix @ P^T      (scene/cameras.py:57-58) */
     const float* campos;      /* (3)    device                        (scene/cameras.py:59) */
+    /* Distance, in floats, between consecutive planes of out_color / out_others (forward) and of
+     * dL_dout_color / dL_dout_others (backward); 0 = image_height * image_width (contiguous (C,H,W), what
+     * upstream allocates).  A larger stride lets the tile-band mode render straight into a frame padded to
+     * equal bands, which an in-place all-gather then completes — no staging or stitch copies. */
+    int64_t out_plane_stride;
+    int64_t grad_plane_stride;
 } surfel_settings_t;
 
 int surfel_abi_version(void);

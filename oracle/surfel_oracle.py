@@ -40,6 +40,11 @@ def lib():
     return _lib
 
 
+def set_threads(n=0):
+    """OpenMP threads used by the oracle's parallel loops (0 = every core); returns the count in force."""
+    return int(lib().oracle_set_threads(int(n)))
+
+
 def _p(a):
     if a is None:
         return None

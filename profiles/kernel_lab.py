@@ -72,7 +72,7 @@ def child(args):
            "Msplats_per_s": round(P / ms_step / 1e3, 1), "R": int(dsr.last_num_rendered()), "stage_ms": stages}
     res = {"color": color.detach(), "allmap": allmap.detach(), "means3D": leaf["means3D"].grad, "shs": leaf["shs"].grad,
            "opacities": leaf["opacities"].grad, "scales": leaf["scales"].grad, "rotations": leaf["rotations"].grad}
-    ref_path = os.path.join(ROOT, "gpurun_out", f"lab_ref_{args.workload}_{P}.pt")
+    ref_path = os.path.join("/tmp", f"lab_ref_{args.workload}_{P}.pt")      # first library's results (not brought back)
     if args.save_ref:
         torch.save({k: v.cpu() for k, v in res.items()}, ref_path)
     elif os.path.exists(ref_path):

@@ -53,9 +53,18 @@ def _worker(rank, world, port, out):
         # the densification proxy is not additive over bands by construction? it is linear in dL_dT: include it
         tens = [torch.from_numpy(grads[k].astype(np.float32)) for k in keys + ["dL_dmeans2D"]]
         SP.allreduce_gradients(tens)
+        # copy-free exchange: padded frame, equal bands, in-place all-gather per plane
+        eb = SP.equal_band(H, rank, world)
+        pre_e, bin_e, img_e = O.forward(sn, cn, bg, row0=eb[0], row1=eb[1])
+        buf = SP.padded_frame(10, H, W, world, "cpu")
+        buf.fill_(float("nan"))
+        es, ee = SP.band_pixel_rows(H, eb)
+        buf[:3, es:ee] = torch.from_numpy(img_e["color"][:, es:ee]); buf[3:, es:ee] = torch.from_numpy(img_e["others"][:, es:ee])
+        SP.allgather_frame_inplace(buf, H, rank, world)
         views = SP.shard_views(5, rank, world)
         if rank == 0:
-            torch.save({"full": full, "grads": dict(zip(keys + ["dL_dmeans2D"], tens)), "views": views, "band": band}, out)
+            torch.save({"full": full, "grads": dict(zip(keys + ["dL_dmeans2D"], tens)), "views": views, "band": band,
+                        "frame_inplace": buf[:, :H].clone(), "equal_band": eb}, out)
         else:
             torch.save({"views": views, "band": band}, out + ".r1")
     finally:
@@ -79,6 +88,8 @@ def test_tile_band_and_view_sharding_world2(oracle, tmp_path):
     pre, binned, img = oracle.forward(sn, cn, bg)
     ref = np.concatenate([img["color"], img["others"]], 0)
     np.testing.assert_array_equal(r0["full"].numpy(), ref)          # stitched frame is bit-identical
+    np.testing.assert_array_equal(r0["frame_inplace"].numpy(), ref)  # and so is the frame completed in place
+    assert r0["equal_band"] == (0, 4)
     gc, go = S.make_cotangents(W, H, 21)
     full = oracle.backward(sn, cn, bg, pre, binned, img, gc.numpy(), go.numpy())
     for k, v in r0["grads"].items():
@@ -98,5 +109,10 @@ def test_band_helpers():
             assert all(bands[i][1] == bands[i + 1][0] for i in range(world - 1))
             assert max(b[1] - b[0] for b in bands) - min(b[1] - b[0] for b in bands) <= 1
     assert SP.shard_views(8, 3, 8) == [3] and SP.shard_views(3, 5, 8) == []
+    for H, world in ((4320, 8), (100, 2), (100, 8), (16, 3)):
+        gy, rp = SP.tile_rows(H), SP.equal_band_rows(H, world)
+        eb = [SP.equal_band(H, r, world) for r in range(world)]
+        assert eb[0][0] == 0 and eb[-1][1] == gy and all(eb[i][1] == eb[i + 1][0] for i in range(world - 1))
+        assert all(b[1] - b[0] <= rp for b in eb) and SP.padded_frame(1, H, 8, world, "cpu").shape[1] == rp * world * 16
     x = torch.arange(2 * 40 * 8, dtype=torch.float32).reshape(2, 40, 8)
     assert torch.equal(SP.gather_band_outputs(x, 40, 0, 1), x)
