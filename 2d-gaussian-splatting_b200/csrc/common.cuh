@@ -40,7 +40,8 @@ constexpr int kChDepth = 0, kChAlpha = 1, kChNormal = 2, kChMidDepth = 5, kChDis
 // formula than upstream's own float32 evaluation.  The ray-splat depth s.x*Tw.x + s.y*Tw.y + Tw.z equals
 // det(T) / p.z exactly (w of the intersection point), which is how the forward evaluates it.
 //   q0 = (P1.x, P1.y, P1.z, c.x)        q1 = (P2.x, P2.y, P2.z, c.y)
-//   q2 = (Pc.x, Pc.y, Pc.z, opacity)    q3 = (n.x, n.y, n.z, Tw.z)          n = view-space normal
+//   q2 = (Pc.x, Pc.y, Pc.z, +-opacity)  q3 = (n.x, n.y, n.z, Tw.z)          n = view-space normal
+//        (opacity < 0: the splat may reach in front of the near plane -> per-pixel `depth < near` test needed)
 //   q4 = (r, g, b, det T)               q5 = (Tw.x, Tw.y, splat index bits, view depth)
 //   q6 = conservative screen AABB (x0, y0, x1, y1) of the region where alpha can reach 1/255
 //   q7 = extents of the same region along the diagonals (min x+y, max x+y, min x-y, max x-y)

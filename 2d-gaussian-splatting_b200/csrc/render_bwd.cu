@@ -15,8 +15,7 @@
 //  * A.4's eight suffix recurrences are collapsed into ONE accumulator S (see below);
 //  * per (warp, splat) the lanes that really contribute (~9 of 32 at 1 M splats / 1080p) are compacted
 //    with a ballot: each writes its 22 partials as one row of a per-warp shared-memory panel, then 22
-//    lanes each add one COLUMN of the panel (a fall-through ladder entered at the row count: two
-//    instructions per row, no loop) and issue ONE red.global.add.f32 into the splat's 96-byte gradient
+//    lanes each add one COLUMN of the panel and issue ONE red.global.add.f32 into the splat's 96-byte gradient
 //    record (layout: common.cuh; the homography gradient is carried as the sums A, Bx, By, Z and finished
 //    in preprocess backward).  Global atomics drop from 18 per (pixel,splat) to 18 per (warp,splat),
 //    contiguous.
@@ -29,34 +28,25 @@ namespace surfel {
 #ifndef SURFEL_BWD_BLOCKS
 #define SURFEL_BWD_BLOCKS 4
 #endif
-#ifndef SURFEL_BWD_SUM
-#define SURFEL_BWD_SUM 2        // column sums: 0 = indexed-branch ladder, 1 = plain loop, 2 = blocks of four
-#endif
 #ifndef SURFEL_BWD_BATCH
-#define SURFEL_BWD_BATCH 352
+#define SURFEL_BWD_BATCH 256
 #endif
 constexpr int kBatchB = SURFEL_BWD_BATCH;         // multiple of 32
 constexpr int kGroupsB = kBatchB / 32;
-constexpr int kPanelRow = 24;                     // 22 used floats; rows 4 apart share banks (rarely both live in a quarter warp)
+constexpr int kPanelRow = 24;                     // 22 used floats.  Rows 4 apart share banks (two-way conflicts on the row stores when a
+                                                  // half warp holds >= 5 live lanes); the conflict-free 28-float stride was measured SLOWER
+                                                  // (0.882 vs 0.865 ms): the 4 KB of shared memory it costs per CTA matter more
 constexpr int kPanelBytes = 8 * 32 * kPanelRow * 4;
 constexpr int kRecBytesB = kRecQuadsFwd * kBatchB * 16;        // the backward stages the same five quads as the forward
 constexpr int kBwdSmemBytes = kRecBytesB + kBatchB * 4 + kPanelBytes + 8 * kGroupsB * 4 + 32;
 
-// acc = sum of the first `cnt` (1..32) rows of this lane's panel column: a fall-through ladder entered
-// through ONE indexed branch (brx.idx; a C++ switch is lowered to a tree of compares by nvcc) — one LDS and
-// one FADD per row, no loop, no per-row control flow.
-static_assert(kPanelRow * 4 == 96, "the ladder below hard-codes the 96-byte row stride");
+// Sum of the first `cnt` (1..32) rows of this lane's panel column: blocks of four rows (independent loads in
+// flight, two partial sums), then the 0-3 leftover rows.  The loops are kept rolled: unrolled by the
+// compiler they turn into a tree of trip-count tests that costs more than the rows themselves at ~9 rows
+// (measured at the headline workload: 0.878 ms this way, 0.893 ms compiler-unrolled, 0.963 ms one row per
+// iteration, 0.958 ms through an indexed-branch ladder — BRX is slow).
 __device__ __forceinline__ float column_sum(uint32_t a, int cnt) {
-    float acc = 0.0f;
-#if SURFEL_BWD_SUM == 1
-#pragma unroll 1
-    for (int r = 0; r < cnt; r++) acc += lds32(a + r * kPanelRow * 4);
-    return acc;
-#elif SURFEL_BWD_SUM == 2
-    // blocks of four rows (independent loads in flight, two partial sums), then the 0-3 leftover rows;
-    // the loops are kept rolled: unrolled by the compiler they turn into a tree of trip-count tests that
-    // costs more than the rows themselves at ~9 rows
-    float acc2 = 0.0f;
+    float acc = 0.0f, acc2 = 0.0f;
     int r = cnt;
 #pragma unroll 1
     for (; r >= 4; r -= 4, a += 4 * kPanelRow * 4) {
@@ -66,47 +56,6 @@ __device__ __forceinline__ float column_sum(uint32_t a, int cnt) {
 #pragma unroll 1
     for (; r > 0; r--, a += kPanelRow * 4) acc += lds32(a);
     return acc + acc2;
-#endif
-    asm volatile(
-        "{\n"
-        "    .reg .f32 t;\n"
-        "    ts: .branchtargets L1, L2, L3, L4, L5, L6, L7, L8, L9, L10, L11, L12, L13, L14, L15, L16, L17, L18, L19, L20, L21, L22, L23, L24, L25, L26, L27, L28, L29, L30, L31, L32;\n"
-        "    brx.idx %2, ts;\n"
-        "L32: ld.shared.f32 t, [%1 + 2976]; add.f32 %0, %0, t;\n"
-        "L31: ld.shared.f32 t, [%1 + 2880]; add.f32 %0, %0, t;\n"
-        "L30: ld.shared.f32 t, [%1 + 2784]; add.f32 %0, %0, t;\n"
-        "L29: ld.shared.f32 t, [%1 + 2688]; add.f32 %0, %0, t;\n"
-        "L28: ld.shared.f32 t, [%1 + 2592]; add.f32 %0, %0, t;\n"
-        "L27: ld.shared.f32 t, [%1 + 2496]; add.f32 %0, %0, t;\n"
-        "L26: ld.shared.f32 t, [%1 + 2400]; add.f32 %0, %0, t;\n"
-        "L25: ld.shared.f32 t, [%1 + 2304]; add.f32 %0, %0, t;\n"
-        "L24: ld.shared.f32 t, [%1 + 2208]; add.f32 %0, %0, t;\n"
-        "L23: ld.shared.f32 t, [%1 + 2112]; add.f32 %0, %0, t;\n"
-        "L22: ld.shared.f32 t, [%1 + 2016]; add.f32 %0, %0, t;\n"
-        "L21: ld.shared.f32 t, [%1 + 1920]; add.f32 %0, %0, t;\n"
-        "L20: ld.shared.f32 t, [%1 + 1824]; add.f32 %0, %0, t;\n"
-        "L19: ld.shared.f32 t, [%1 + 1728]; add.f32 %0, %0, t;\n"
-        "L18: ld.shared.f32 t, [%1 + 1632]; add.f32 %0, %0, t;\n"
-        "L17: ld.shared.f32 t, [%1 + 1536]; add.f32 %0, %0, t;\n"
-        "L16: ld.shared.f32 t, [%1 + 1440]; add.f32 %0, %0, t;\n"
-        "L15: ld.shared.f32 t, [%1 + 1344]; add.f32 %0, %0, t;\n"
-        "L14: ld.shared.f32 t, [%1 + 1248]; add.f32 %0, %0, t;\n"
-        "L13: ld.shared.f32 t, [%1 + 1152]; add.f32 %0, %0, t;\n"
-        "L12: ld.shared.f32 t, [%1 + 1056]; add.f32 %0, %0, t;\n"
-        "L11: ld.shared.f32 t, [%1 + 960]; add.f32 %0, %0, t;\n"
-        "L10: ld.shared.f32 t, [%1 + 864]; add.f32 %0, %0, t;\n"
-        "L9: ld.shared.f32 t, [%1 + 768]; add.f32 %0, %0, t;\n"
-        "L8: ld.shared.f32 t, [%1 + 672]; add.f32 %0, %0, t;\n"
-        "L7: ld.shared.f32 t, [%1 + 576]; add.f32 %0, %0, t;\n"
-        "L6: ld.shared.f32 t, [%1 + 480]; add.f32 %0, %0, t;\n"
-        "L5: ld.shared.f32 t, [%1 + 384]; add.f32 %0, %0, t;\n"
-        "L4: ld.shared.f32 t, [%1 + 288]; add.f32 %0, %0, t;\n"
-        "L3: ld.shared.f32 t, [%1 + 192]; add.f32 %0, %0, t;\n"
-        "L2: ld.shared.f32 t, [%1 + 96]; add.f32 %0, %0, t;\n"
-        "L1: ld.shared.f32 t, [%1 + 0]; add.f32 %0, %0, t;\n"
-        "}\n"
-        : "+f"(acc) : "r"(a), "r"(cnt - 1));
-    return acc;
 }
 
 __global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(RenderParams p) {
@@ -241,7 +190,7 @@ __global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(Rend
                     const uint32_t ro = panel_base + (uint32_t)__popc(am & lt_mask) * (kPanelRow * 4);
                     // A.3's `depth < near` skip (rare: splats reaching through the near plane): the pair was not
                     // blended, so it leaves T and S alone and contributes a row of zeros
-                    if (__builtin_expect(depth < kNear, 0)) {
+                    if (q2.w < 0.0f && depth < kNear) {            // flagged splats only (warp-uniform flag)
                         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
                         sts128(ro, z4); sts128(ro + 16, z4); sts128(ro + 32, z4); sts128(ro + 48, z4); sts128(ro + 64, z4);
                         sts64(ro + 80, 0.f, 0.f);
@@ -262,7 +211,7 @@ __global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(Rend
                         S = fmaf(w, v, S);
                         float dL_dz = ((int)j == med) ? dL_dmedian : 0.0f;
                         dL_dz = fmaf(w * dmd_dd, fmaf(m_d, Ar2, nD1r2), dL_dz);
-                        const float dL_dG = q2.w * dL_dalpha;
+                        const float dL_dG = fabsf(q2.w) * dL_dalpha;
                         dL_dz = fmaf(w, dL_ddepth, dL_dz);
                         const float dop = G * dL_dalpha;
                         if (use3d) {
@@ -287,14 +236,13 @@ __global__ void __launch_bounds__(256, SURFEL_BWD_BLOCKS) render_bwd_kernel(Rend
                         sts64(ro + 80, w * dpix1, w * dpix2);
                     }
                 }
+                const uint32_t id = lds32u(idb + j * 4u);          // requested before the column sums need it
                 __syncwarp();
                 {
-                    // every lane sums a column (lanes 22..31 read row padding / the head of the next row — inside
-                    // the panel's allocation — and drop the result): the loop runs converged, with a warp-uniform
-                    // trip count
-                    const float acc = column_sum(panel_base + (uint32_t)__popc(lt_mask) * 4u, __popc(am));
+                    // every lane sums a column (lanes 24..31 re-read column 23, padding, and drop the result): the
+                    // loop runs converged, with a warp-uniform trip count
+                    const float acc = column_sum(panel_base + (uint32_t)min(__popc(lt_mask), kPanelRow - 1) * 4u, __popc(am));
                     if (lane < kGradUsed && acc != 0.0f) {
-                        const uint32_t id = lds32u(idb + j * 4u);
                         atomicAdd(p.grad_rec + (size_t)id * kGradFloats + lane, acc);
                     }
                 }

@@ -34,7 +34,8 @@ __device__ __forceinline__ float fast_ex2(float x) {
 //   q0 = (P1.x, P1.y, P1.z, c.x)   q1 = (P2.x, P2.y, P2.z, c.y)   q2 = (Pc.x, Pc.y, Pc.z, opacity)
 // Returns false when the pair is skipped by A.3's `p.z == 0` or `alpha < 1/255` tests.  The remaining
 // A.3 `continue` tests: `power > 0` cannot fire (rho >= 0 or NaN, and NaN compares false upstream as
-// well); `depth < near` is applied by the callers once the depth is known (live lanes only).
+// well); `depth < near` is applied by the callers once the depth is known, and only for splats that
+// preprocess flagged (negative stored opacity) as able to reach in front of the near plane.
 // Every operation is an explicit round-to-nearest intrinsic so that forward and backward (separate
 // translation units) take bit-identical decisions for a pair.
 __device__ __forceinline__ bool eval_pair(float pxf, float pyf, const float4& q0, const float4& q1,
@@ -50,7 +51,7 @@ __device__ __forceinline__ bool eval_pair(float pxf, float pyf, const float4& q0
     e.rho2d = __fadd_rn(h, h);                                   // FilterInvSquare = 2
     const float rho = fminf(e.rho3d, e.rho2d);
     e.G = fast_ex2(__fmul_rn(rho, -0.72134752044448170368f));    // exp(-0.5 rho)
-    e.alpha = fminf(kAlphaMax, __fmul_rn(q2.w, e.G));
+    e.alpha = fminf(kAlphaMax, __fmul_rn(fabsf(q2.w), e.G));     // |.|: the sign of the stored opacity is the near-plane flag
     return !(e.alpha < kAlphaMin) && e.pz != 0.0f;
 }
 

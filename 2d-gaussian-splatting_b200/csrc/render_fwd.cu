@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(256, SURFEL_FWD_BLOCKS) render_fwd_kernel(Rend
                         const float4 q3 = lds128(ra + 3 * kBatch * 16), q4 = lds128(ra + 4 * kBatch * 16);
                         // ray-splat depth = w of the intersection = det T / p.z; low-pass branch: Tw.z
                         const float depth = (e.rho3d <= e.rho2d) ? q4.w * e.inv_pz : q3.w;
-                        if (depth < kNear) continue;
+                        if (q2.w < 0.0f && depth < kNear) continue;    // flagged splats only (warp-uniform flag)
                         const float test_T = T * (1.0f - e.alpha);
                         if (test_T < kTMin) { last_contributor |= 0x80000000u; break; }
                         const uint32_t contributor = k32 - hb;   // 1-based list position

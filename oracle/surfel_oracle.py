@@ -125,12 +125,14 @@ def render_fwd(pre, binned, bg, W, H, f64=False):
     return out
 
 
-def render_bwd(pre, binned, img, bg, dL_dcolor, dL_dothers, W, H, lowpass_quirk=True):
+def render_bwd(pre, binned, img, bg, dL_dcolor, dL_dothers, W, H, lowpass_quirk=True, f64=False):
+    """A.4.  f64=True: the per-pair arithmetic in double (yardstick for float32 rounding noise, not a parity target)."""
     P = pre["radii"].shape[0]
     out = dict(dL_dtransMat=np.zeros((P, 9), np.float64), dL_dmean2D=np.zeros((P, 2), np.float64),
                dL_dopacity=np.zeros(P, np.float64), dL_dnormal=np.zeros((P, 3), np.float64),
                dL_dcolors=np.zeros((P, 3), np.float64))
-    lib().oracle_render_bwd(W, H, _p(binned["ranges"]), _p(binned["vals_sorted"]), _p(pre["xy"]),
+    fn = lib().oracle_render_bwd_f64 if f64 else lib().oracle_render_bwd
+    fn(W, H, _p(binned["ranges"]), _p(binned["vals_sorted"]), _p(pre["xy"]),
                             _p(pre["transMat"]), _p(pre["normal_opacity"]), _p(pre["rgb"]),
                             _p(_f32(bg)), _p(img["accum"]), _p(img["n_contrib"]),
                             _p(_f32(dL_dcolor)), _p(_f32(dL_dothers)), int(bool(lowpass_quirk)),
@@ -179,9 +181,9 @@ def forward(scene, cam, bg, sh_degree=3, scale_modifier=1.0, row0=0, row1=None):
 
 
 def backward(scene, cam, bg, pre, binned, img, dL_dcolor, dL_dothers, sh_degree=3,
-             scale_modifier=1.0, lowpass_quirk=True):
+             scale_modifier=1.0, lowpass_quirk=True, f64=False):
     W, H = cam["W"], cam["H"]
-    rb = render_bwd(pre, binned, img, bg, dL_dcolor, dL_dothers, W, H, lowpass_quirk)
+    rb = render_bwd(pre, binned, img, bg, dL_dcolor, dL_dothers, W, H, lowpass_quirk, f64)
     return preprocess_bwd(scene["means3D"], scene.get("scales"), scene.get("rotations"),
                           scene.get("shs"), pre, rb, cam["viewmatrix"], cam["projmatrix"],
                           cam["campos"], W, H, sh_degree, scale_modifier,

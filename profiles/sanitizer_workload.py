@@ -27,5 +27,4 @@ def run(P,W,H,variant=None):
     print('ok',P,W,H,variant, float(loss.detach()))
 run(3000,200,136)
 run(700,100,70,("sort","radix","bucket"))
-run(700,100,70,("render_bwd","tma","classic"))
-run(700,100,70,("render_fwd","g8","warp"))
+run(9000,160,120)      # ~500-entry tile lists: the render kernels take a second staging round

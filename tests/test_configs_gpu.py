@@ -13,7 +13,8 @@ import pytest
 import torch
 
 import surfel_scenes as S
-from test_parity_gpu import assert_close_budget, grad_check, record_stats, FLIP_BUDGET
+from parity_bars import (GRAD_TOL, GRAD_BUDGET_EXACT, NOISE_FACTOR, NOISE_FLOOR, OUT_TOL, OUT_BUDGET_EXACT, record_stats,
+                         rel_grad as _rel_grad, rel_out as _rel_out, two_bar_check)
 
 pytestmark = pytest.mark.gpu
 
@@ -41,7 +42,7 @@ def regularizer_cotangents(color, allmap, cam, depth_ratio=1.0, lam_ssim=0.2, la
     return (gc * s).cpu().numpy(), (ga * s).cpu().numpy()
 
 
-def run_config(oracle, name, rows=None, regularizers=False, budget=FLIP_BUDGET):
+def run_config(oracle, name, rows=None, regularizers=False):
     from cuda_stages import CudaPipeline
     scene, cam = S.named(name)
     scene, cam = S.to_numpy(scene), S.to_numpy(cam)
@@ -66,26 +67,16 @@ def run_config(oracle, name, rows=None, regularizers=False, budget=FLIP_BUDGET):
     gi = pipe.render()
     ys = slice(r0 * 16, min(H, r1 * 16))
     print(f"{name}: P={pre['radii'].size} visible={int(vis.sum())} R={gp['R']} rows [{r0},{r1}) of {gy}")
-    assert_close_budget("color", gi["color"][:, ys], img["color"][:, ys], budget=budget)
-    for ch, nm in enumerate(["depth", "alpha", "nx", "ny", "nz", "median_depth", "distortion"]):
-        assert_close_budget(nm, gi["others"][ch, ys], img["others"][ch, ys], budget=budget)
-    same = (gi["n_contrib"][:, ys] == img["n_contrib"][:, ys]).mean()
-    print(f"n_contrib / median contributor identical on {same:.6f} of pixels")
-    assert same >= 1.0 - budget
-    # Yardstick (reported, and bounded by the same budget): the exact-arithmetic value of the published
-    # formula (oracle in double on the same float32 inputs).  k = px*Tw - Tu cancels terms of order
-    # |pixel|*depth, so the float32 oracle itself (like upstream's float32 kernel) is only accurate to
-    # ~1e-5..1e-4 there; the CUDA path evaluates the same intersection about the splat's own screen
-    # position and must be at least as close to the exact value as the float32 oracle is.
     i64 = oracle.render_fwd(pre, binned, bg, W, H, f64=True)
-    for nm, a, b in (("color", gi["color"], img["color"]), ("allmap", gi["others"], img["others"])):
-        k = "color" if nm == "color" else "others"
-        e_gpu = np.abs(a[:, ys].astype(np.float64) - i64[k][:, ys]) / np.maximum(1.0, np.abs(i64[k][:, ys]))
-        e_f32 = np.abs(b[:, ys].astype(np.float64) - i64[k][:, ys]) / np.maximum(1.0, np.abs(i64[k][:, ys]))
-        sg = record_stats(f"{nm}: CUDA vs float64 evaluation", e_gpu, dict(frac_outside=float((e_gpu > 1e-4).mean()), tol=1e-4))
-        sf = record_stats(f"{nm}: float32 oracle vs float64 evaluation", e_f32, dict(frac_outside=float((e_f32 > 1e-4).mean()), tol=1e-4))
-        assert sg["frac_outside"] <= budget
-        assert sg["p999"] <= max(2.0 * sf["p999"], 2e-5), "the CUDA path is further from the exact value than float32 rounding explains"
+    two_bar_check("color", gi["color"][:, ys], img["color"][:, ys], i64["color"][:, ys], _rel_out, OUT_TOL, OUT_BUDGET_EXACT)
+    for ch, nm in enumerate(["depth", "alpha", "nx", "ny", "nz", "median_depth", "distortion"]):
+        two_bar_check(nm, gi["others"][ch, ys], img["others"][ch, ys], i64["others"][ch, ys], _rel_out, OUT_TOL, OUT_BUDGET_EXACT)
+    same64 = (gi["n_contrib"][:, ys] == i64["n_contrib"][:, ys]).mean()
+    same32 = (gi["n_contrib"][:, ys] == img["n_contrib"][:, ys]).mean()
+    noise = (img["n_contrib"][:, ys] == i64["n_contrib"][:, ys]).mean()
+    print(f"n_contrib / median contributor identical to the exact evaluation on {same64:.7f} of pixels, to the float32 oracle on "
+          f"{same32:.7f} (float32 oracle vs exact: {noise:.7f})")
+    assert same64 >= 1.0 - OUT_BUDGET_EXACT and (1.0 - same32) <= NOISE_FACTOR * (1.0 - noise) + NOISE_FLOOR
     if regularizers:
         gc, go = regularizer_cotangents(gi["color"], gi["others"], cam)
     else:
@@ -94,13 +85,16 @@ def run_config(oracle, name, rows=None, regularizers=False, budget=FLIP_BUDGET):
     gcb[:, ys], gob[:, ys] = gc[:, ys], go[:, ys]          # a band's cotangents are the frame's, sliced
     # oracle backward replayed on the GPU's own forward state (a flipped threshold pixel in the forward
     # must not masquerade as a backward error)
-    img_gpu = dict(accum=gi["accum"], n_contrib=gi["n_contrib"])
+    # (outside the band the image workspace is whatever the caller left there — the stage harness poisons it)
+    acc_b, nc_b = np.zeros_like(gi["accum"]), np.zeros_like(gi["n_contrib"])
+    acc_b[:, ys], nc_b[:, ys] = gi["accum"][:, ys], gi["n_contrib"][:, ys]
+    img_gpu = dict(accum=acc_b, n_contrib=nc_b)
     ref = oracle.backward(scene, cam, bg, pre, binned, img_gpu, gcb, gob)
+    ref64 = oracle.backward(scene, cam, bg, pre, binned, img_gpu, gcb, gob, f64=True)
     got = pipe.backward(gcb, gob)
     for k in ("dL_dmeans3D", "dL_dscales", "dL_drotations", "dL_dopacity", "dL_dshs", "dL_dmeans2D"):
-        assert np.isfinite(got[k]).all(), k
         assert (got[k][~vis] == 0).all(), f"{k}: culled splats must have zero gradient"
-        grad_check(k, got[k], ref[k])
+        two_bar_check(k, got[k], ref[k], ref64[k], _rel_grad, GRAD_TOL, GRAD_BUDGET_EXACT)
 
 
 def test_headline_full_frame(oracle, cuda_lib):
