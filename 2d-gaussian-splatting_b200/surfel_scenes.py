@@ -83,7 +83,20 @@ def look_at_rotation(yaw_deg, pitch_deg):
 
 def make_scene(P, W, H, seed, fovy_deg=50.0, depth_complexity=30.0, sh_coeffs=16, sigma_scale=1.0):
     """§8(d) generator.  Returns CPU float32 tensors: means3D (P,3), scales (P,2), rotations (P,4),
-    opacities (P,1), shs (P,16,3).  Positions are in the frame of the identity camera."""
+    opacities (P,1), shs (P,16,3).  Positions are in the frame of the identity camera.
+    Generated on ONE thread: PyTorch's vectorised CPU kernels (exp, sigmoid, norm) round the elements at the
+    seams of its per-thread chunks differently, so with the intra-op thread count of the moment the "same"
+    scene differed in the last bit of a few values — enough to flip alpha >= 1/255 decisions between two
+    processes (seen as a 1e-2-sized difference between two A/B runs in profiles/kernel_lab.py)."""
+    nthreads = torch.get_num_threads()
+    torch.set_num_threads(1)
+    try:
+        return _make_scene(P, W, H, seed, fovy_deg, depth_complexity, sh_coeffs, sigma_scale)
+    finally:
+        torch.set_num_threads(nthreads)
+
+
+def _make_scene(P, W, H, seed, fovy_deg, depth_complexity, sh_coeffs, sigma_scale):
     g = torch.Generator("cpu").manual_seed(1234 + seed)
 
     def U(n, lo, hi):
