@@ -151,19 +151,23 @@ class _BandFrame(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                 settings, rank, world, group, grad_reduce):
-        from diff_surfel_rasterization import _RasterizeGaussians
+        from diff_surfel_rasterization import _RasterizeGaussians, _mark
         H, W = int(settings.image_height), int(settings.image_width)
+        _mark("band_enter")
         buf = padded_frame(10, H, W, world, means3D.device)
+        _mark("band_frame_allocated")
         band = equal_band(H, rank, world)
         rs = settings._replace(tile_rows=band, out_buffers=(buf[:3, :H], buf[3:, :H]))
         color, radii, allmap = _RasterizeGaussians.forward(ctx, means3D, means2D, sh, colors_precomp, opacities,
                                                            scales, rotations, cov3Ds_precomp, rs)
         allgather_frame_inplace(buf, H, rank, world, group)
+        _mark("band_gather_enqueued")
         _last["frame"] = buf
         if world > 1 and dist.is_initialized():
             # radii (and so visibility_filter / max_radii2D downstream) are per-band partials: a splat's tile
             # rect is clipped to the band before it is counted
             dist.all_reduce(radii, op=dist.ReduceOp.MAX, group=group)
+        _mark("band_exit")
         ctx.band_meta = (world, group, grad_reduce)
         return color, radii, allmap
 
