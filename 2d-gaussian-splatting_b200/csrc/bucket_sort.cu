@@ -83,20 +83,26 @@ tile_count_kernel(int P, int gx, int gy, int row0, int row1, const float4* __res
 }
 
 // One block: exclusive scan of tile_count -> ranges; zero the fill cursors; collect big tiles.
+// Four consecutive tiles per thread and round (4096 tiles per round: two rounds for a 1920x1080 frame, 32 for
+// 7680x4320), warp scans for both levels, the running carry kept in a register by every thread: two barriers
+// per round.
 __global__ void __launch_bounds__(1024)
 tile_scan_kernel(int tiles, uint32_t cap, const uint32_t* __restrict__ tile_count, uint2* __restrict__ ranges,
                  uint32_t* __restrict__ tile_fill, uint32_t* __restrict__ big_list,
                  uint32_t* __restrict__ big_count, uint32_t* __restrict__ mid_list,
                  uint32_t* __restrict__ mid_count) {
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
+    __shared__ uint32_t s_warp[32], s_warp_ex[32];
+    __shared__ uint32_t s_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) { s_carry = 0; *big_count = 0; *mid_count = 0; }
-    __syncthreads();
-    for (int base = 0; base < tiles; base += 1024) {
-        const int t = base + tid;
-        const uint32_t c = t < tiles ? tile_count[t] : 0u;
-        uint32_t incl = c;
+    if (tid == 0) { *big_count = 0; *mid_count = 0; }
+    uint32_t carry = 0;
+    for (int base = 0; base < tiles; base += 4096) {
+        const int t0 = base + tid * 4;
+        uint32_t c[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) c[k] = t0 + k < tiles ? tile_count[t0 + k] : 0u;
+        const uint32_t sum = c[0] + c[1] + c[2] + c[3];
+        uint32_t incl = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
@@ -104,23 +110,37 @@ tile_scan_kernel(int tiles, uint32_t cap, const uint32_t* __restrict__ tile_coun
         }
         if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
-        uint32_t pre = s_carry;
-        for (int w = 0; w < warp; w++) pre += s_warp[w];
-        if (t < tiles) {
-            // `cap` = number of instance slots the caller allocated.  When the forward is launched
-            // speculatively with a capacity guess (no host sync on R) and the guess was too small,
-            // everything is clamped so that no kernel touches memory past the buffers; the host then
-            // sees R > cap and re-runs with exact sizes.
-            const uint32_t start = min(pre + incl - c, cap), end = min(pre + incl, cap);
-            const uint32_t cc = end - start;
-            ranges[t] = cc ? make_uint2(start, end) : make_uint2(0u, 0u);
-            tile_fill[t] = pre + incl - c;
-            if (cc > (uint32_t)kSmallMax) big_list[atomicAdd(big_count, 1u)] = (uint32_t)t;
-            else if (cc > (uint32_t)kWarpMax) mid_list[atomicAdd(mid_count, 1u)] = (uint32_t)t;
+        if (warp == 0) {
+            const uint32_t v = s_warp[lane];
+            uint32_t vi = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, vi, o);
+                if (lane >= o) vi += u;
+            }
+            s_warp_ex[lane] = vi - v;
+            if (lane == 31) s_total = vi;
         }
         __syncthreads();
-        if (tid == 1023) s_carry = pre + incl;
-        __syncthreads();
+        uint32_t pre = carry + s_warp_ex[warp] + incl - sum;       // exclusive prefix of this thread's first tile
+        carry += s_total;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int t = t0 + k;
+            if (t < tiles) {
+                // `cap` = number of instance slots the caller allocated.  When the forward is launched
+                // speculatively with a capacity guess (no host sync on R) and the guess was too small,
+                // everything is clamped so that no kernel touches memory past the buffers; the host then
+                // sees R > cap and re-runs with exact sizes.
+                const uint32_t start = min(pre, cap), end = min(pre + c[k], cap);
+                const uint32_t cc = end - start;
+                ranges[t] = cc ? make_uint2(start, end) : make_uint2(0u, 0u);
+                tile_fill[t] = pre;
+                if (cc > (uint32_t)kSmallMax) big_list[atomicAdd(big_count, 1u)] = (uint32_t)t;
+                else if (cc > (uint32_t)kWarpMax) mid_list[atomicAdd(mid_count, 1u)] = (uint32_t)t;
+            }
+            pre += c[k];
+        }
     }
 }
 

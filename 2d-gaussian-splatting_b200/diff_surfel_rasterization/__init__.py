@@ -267,7 +267,11 @@ class _RasterizeGaussians(torch.autograd.Function):
                     img.data_ptr(), int(P > 0), color.data_ptr(), allmap.data_ptr(), stream))
 
         _last["num_rendered"] = R
-        ctx.raster_settings = rs
+        # NOT the caller's out_buffers: they are this node's outputs, and an output held by its own grad_fn's
+        # context is a reference cycle — the frame (and everything else the context holds: workspaces, the
+        # gradient bucket) would live until the cyclic garbage collector happens to run (measured: +1.8 GB of
+        # reserved device memory and two cudaMalloc calls per config-5 step, profiles/r2_band_probe.md)
+        ctx.raster_settings = rs._replace(out_buffers=None) if outb is not None else rs
         ctx.num_rendered = cap        # the workspace layout was carved for `cap` instance slots
         ctx.M = M
         ctx.flags = (sh is not None, colors_precomp is not None, scales is not None, cov3Ds_precomp is not None)

@@ -121,21 +121,27 @@ def padded_frame(C: int, H: int, W: int, world: int, device, dtype=torch.float32
     return torch.empty((C, equal_band_rows(H, world) * world * TILE, W), device=device, dtype=dtype)
 
 
-def allgather_frame_inplace(buf: torch.Tensor, H: int, rank: int, world: int, group=None) -> None:
-    """Completes a padded frame (C, H_pad, W) in which this rank has written its own band."""
+def allgather_frame_inplace(buf: torch.Tensor, H: int, rank: int, world: int, group=None, async_op: bool = False):
+    """Completes a padded frame (C, H_pad, W) in which this rank has written its own band.  With async_op the
+    collectives are only enqueued (on the backend's own stream, ordered after the work already queued on the
+    current stream) and the list of work handles is returned: the caller's stream does not wait for them."""
     if world == 1 or not dist.is_initialized():
-        return
+        return []
     C, Hp, W = buf.shape
     rows = Hp // world
+    works = []
     for c in range(C):
         plane = buf[c]
         send = plane[rank * rows:(rank + 1) * rows].reshape(-1)
         if not buf.is_cuda:
             send = send.clone()          # gloo (CPU tests) does not take an aliased send buffer
-        dist.all_gather_into_tensor(plane.reshape(-1), send, group=group)
+        w = dist.all_gather_into_tensor(plane.reshape(-1), send, group=group, async_op=async_op)
+        if async_op:
+            works.append(w)
+    return works
 
 
-_last = {"grad_bucket": None, "frame": None}
+_last = {"grad_bucket": None, "frame": None, "works": []}
 
 
 def last_exchange_buffers():
@@ -150,7 +156,7 @@ class _BandFrame(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                settings, rank, world, group, grad_reduce):
+                settings, rank, world, group, grad_reduce, gather="sync"):
         from diff_surfel_rasterization import _RasterizeGaussians, _mark
         H, W = int(settings.image_height), int(settings.image_width)
         _mark("band_enter")
@@ -160,7 +166,7 @@ class _BandFrame(torch.autograd.Function):
         rs = settings._replace(tile_rows=band, out_buffers=(buf[:3, :H], buf[3:, :H]))
         color, radii, allmap = _RasterizeGaussians.forward(ctx, means3D, means2D, sh, colors_precomp, opacities,
                                                            scales, rotations, cov3Ds_precomp, rs)
-        allgather_frame_inplace(buf, H, rank, world, group)
+        _last["works"] = allgather_frame_inplace(buf, H, rank, world, group, async_op=(gather == "async"))
         _mark("band_gather_enqueued")
         _last["frame"] = buf
         if world > 1 and dist.is_initialized():
@@ -179,25 +185,40 @@ class _BandFrame(torch.autograd.Function):
         _last["grad_bucket"] = ctx.grad_bucket
         if grad_reduce == "all_reduce" and world > 1 and dist.is_initialized():
             dist.all_reduce(ctx.grad_bucket, op=dist.ReduceOp.SUM, group=group)   # every gradient, one collective, in place
-        return grads[:8] + (None, None, None, None, None)
+        return grads[:8] + (None, None, None, None, None, None)
 
 
 def rasterize_tile_band(rasterizer_cls, settings, rank: int, world: int, group=None, grad_reduce: str = "all_reduce",
-                        **inputs) -> Dict[str, torch.Tensor]:
+                        gather: str = "sync", **inputs) -> Dict[str, torch.Tensor]:
     """One oversized frame split over `world` GPUs (BASELINE config 5).  Returns the COMPLETE
     frame on every rank ("render" (3,H,W), "allmap" (7,H,W): views of one padded tensor), "radii" reduced
     with MAX over the ranks, and the band this rank rendered.  Differentiable; with grad_reduce="all_reduce"
     (default) the gradients that reach the inputs are already summed over the ranks; "none" leaves this
     band's partial sums (the caller reduces them, e.g. with a reduce-scatter for a sharded optimizer).
+
+    gather="async" only ENQUEUES the all-gathers: the rows of this rank's own band (result["band"]) are valid on
+    the current stream at once, the other ranks' rows after result["wait"]() — so a loss that is local to the
+    band (per-pixel terms; SSIM with a 5-row halo inside the band) can run its backward, which reads nothing
+    but this band's cotangent rows, while the exchange is still in flight.
     `rasterizer_cls` is accepted for symmetry with the single-GPU call and is not used."""
     del rasterizer_cls
     if grad_reduce not in ("all_reduce", "none"):
         raise ValueError("grad_reduce must be 'all_reduce' or 'none'")
+    if gather not in ("sync", "async"):
+        raise ValueError("gather must be 'sync' or 'async'")
     empty = torch.Tensor([])
     g = lambda k: inputs.get(k) if inputs.get(k) is not None else empty
     if (inputs.get("shs") is None) == (inputs.get("colors_precomp") is None):
         raise Exception("Please provide excatly one of either SHs or precomputed colors!")
     color, radii, allmap = _BandFrame.apply(inputs["means3D"], inputs["means2D"], g("shs"), g("colors_precomp"),
                                             inputs["opacities"], g("scales"), g("rotations"), g("cov3D_precomp"),
-                                            settings, rank, world, group, grad_reduce)
-    return {"render": color, "allmap": allmap, "radii": radii, "band": equal_band(int(settings.image_height), rank, world)}
+                                            settings, rank, world, group, grad_reduce, gather)
+    works = _last["works"]
+
+    def wait():
+        for w in works:
+            w.wait()
+        del works[:]
+
+    return {"render": color, "allmap": allmap, "radii": radii, "band": equal_band(int(settings.image_height), rank, world),
+            "wait": wait}

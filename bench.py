@@ -274,6 +274,7 @@ def tile_band_leg(rank, world, dev, steps=6, warmup=2, workload="config5"):
     gc, go = gc.to(dev), go.to(dev)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
     acc = [0.0] * 6
+    acc_ov = {"all_reduce": 0.0, "reduce_scatter": 0.0}
 
     def step(timed):
         for t in list(leaf.values()) + [m2d]:
@@ -303,6 +304,28 @@ def tile_band_leg(rank, world, dev, steps=6, warmup=2, workload="config5"):
                 acc[i] += ev[a].elapsed_time(ev[b])
         return res
 
+    def step_overlapped(reduce):
+        """The same frame with the exchange taken off the critical path: the all-gathers are only enqueued, the band
+        backward (which reads this band's cotangent rows only) runs while they are in flight, then the gradient
+        reduction.  What a band-local loss permits; the full frame is complete at the end of the step."""
+        for t in list(leaf.values()) + [m2d]:
+            t.grad = None
+        ev[0].record()
+        res = SP.rasterize_tile_band(GaussianRasterizer, rs, rank, world, grad_reduce="none", gather="async",
+                                     means3D=leaf["means3D"], means2D=m2d, shs=leaf["shs"], opacities=leaf["opacities"],
+                                     scales=leaf["scales"], rotations=leaf["rotations"])
+        torch.autograd.backward([res["render"], res["allmap"]], [gc, go])
+        _, bucket = SP.last_exchange_buffers()
+        if reduce == "all_reduce":
+            dist.all_reduce(bucket)
+        else:
+            dist.reduce_scatter_tensor(torch.empty(bucket.numel() // world, device=dev), bucket)
+        res["wait"]()                                                        # the frame is complete on this stream
+        ev[1].record()
+        torch.cuda.synchronize()
+        acc_ov[reduce] += ev[0].elapsed_time(ev[1])
+        return res
+
     import ctypes
     import time as _time
     from diff_surfel_rasterization import _cabi
@@ -319,14 +342,24 @@ def tile_band_leg(rank, world, dev, steps=6, warmup=2, workload="config5"):
     t_host = (_time.perf_counter() - t_host) / steps * 1e3
     lib.surfel_profile_enable(0); lib.surfel_profile_read(ms_arr, cnt_arr)
     kernels = {lib.surfel_profile_stage_name(i).decode(): round(ms_arr[i] / steps, 3) for i in range(nst) if cnt_arr[i]}
-    tt = torch.tensor([a / steps for a in acc], device=dev, dtype=torch.float64)
+    bucket_divisible = SP.last_exchange_buffers()[1].numel() % world == 0
+    for mode in ("all_reduce",) + (("reduce_scatter",) if bucket_divisible else ()):
+        step_overlapped(mode); acc_ov[mode] = 0.0                            # one untimed step per mode
+        dist.barrier(); torch.cuda.synchronize()
+        for _ in range(steps):
+            res_ov = step_overlapped(mode)
+    tt = torch.tensor([a / steps for a in acc] + [acc_ov["all_reduce"] / steps, acc_ov["reduce_scatter"] / steps],
+                      device=dev, dtype=torch.float64)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    fwd_total, bwd, allreduce, gather, rscatter, frame = (float(x) for x in tt)
+    fwd_total, bwd, allreduce, gather, rscatter, frame, frame_ov, frame_ov_rs = (float(x) for x in tt)
     out = {"workload": f"{workload}: {P} surfels, one {W}x{H} frame in {world} tile-row bands",
            "ms_frame": frame, "ms_band_fwd": max(0.0, fwd_total - gather), "ms_allgather": gather, "ms_band_bwd": bwd,
            "ms_allreduce": allreduce, "ms_reduce_scatter_alternative": rscatter,
            "gather_bytes_per_rank": int(10 * 4 * W * SP.equal_band_rows(H, world) * 16),
            "grad_bytes": int(SP.last_exchange_buffers()[1].numel() * 4),
+           "ms_frame_overlapped": frame_ov, "ms_frame_overlapped_reduce_scatter": frame_ov_rs if bucket_divisible else None,
+           "overlapped": "all-gathers enqueued asynchronously and hidden behind the band backward (band-local cotangents), "
+                         "then the gradient all-reduce / reduce-scatter; full frame complete at the end of the step",
            "Msplats_per_s": P / frame / 1e3, "steps": steps, "kernel_ms_rank0": kernels, "host_ms_per_step_rank0": t_host,
            "how": "padded frame, bands rendered in place, one in-place all_gather_into_tensor per plane; cotangents read in "
                   "place; one all_reduce of the flat gradient bucket (reduce-scatter timed as the sharded-optimizer alternative)"}
@@ -336,7 +369,8 @@ def tile_band_leg(rank, world, dev, steps=6, warmup=2, workload="config5"):
             color, radii, allmap = GaussianRasterizer(rs)(means3D=leaf["means3D"], means2D=m2d, shs=leaf["shs"],
                                                           opacities=leaf["opacities"], scales=leaf["scales"], rotations=leaf["rotations"])
         out["stitched_equals_single_gpu"] = bool(torch.equal(res["render"], color) and torch.equal(res["allmap"], allmap)
-                                                 and torch.equal(res["radii"], radii))
+                                                 and torch.equal(res["radii"], radii)
+                                                 and torch.equal(res_ov["render"], color) and torch.equal(res_ov["allmap"], allmap))
     dist.barrier()
     return out
 

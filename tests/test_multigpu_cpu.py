@@ -61,6 +61,14 @@ def _worker(rank, world, port, out):
         es, ee = SP.band_pixel_rows(H, eb)
         buf[:3, es:ee] = torch.from_numpy(img_e["color"][:, es:ee]); buf[3:, es:ee] = torch.from_numpy(img_e["others"][:, es:ee])
         SP.allgather_frame_inplace(buf, H, rank, world)
+        buf2 = SP.padded_frame(10, H, W, world, "cpu")
+        buf2.fill_(float("nan"))
+        buf2[:, es:ee] = buf[:, es:ee]
+        works = SP.allgather_frame_inplace(buf2, H, rank, world, async_op=True)     # enqueue only ...
+        assert len(works) == 10
+        for w in works:                                                              # ... complete on wait()
+            w.wait()
+        assert torch.equal(buf2[:, :H], buf[:, :H])
         views = SP.shard_views(5, rank, world)
         if rank == 0:
             torch.save({"full": full, "grads": dict(zip(keys + ["dL_dmeans2D"], tens)), "views": views, "band": band,
