@@ -37,9 +37,15 @@ def regularizer_cotangents(color, allmap, cam, depth_ratio=1.0, lam_ssim=0.2, la
     loss = loss + lam_n * (1 - (o["rend_normal"] * o["surf_normal"]).sum(dim=0))[None].mean() + lam_d * o["rend_dist"].mean()
     loss.backward()
     gc, ga = c.grad, torch.nan_to_num(a.grad, 0.0, 0.0, 0.0)      # D/alpha at alpha = 0: the reference's gradient is NaN there
-    # the loss is a mean over ~2 M pixels: scale the cotangents to O(1) so the comparison is not about denormal-sized numbers
-    s = 1.0 / max(float(gc.abs().max()), float(ga.abs().max()), 1e-30)
-    return (gc * s).cpu().numpy(), (ga * s).cpu().numpy()
+    gc, ga = gc.cpu().numpy(), ga.cpu().numpy()
+    # The loss is a mean over ~2 M pixels, so every cotangent is O(1e-7..1e-4): bring them to O(1).  With the
+    # reference's weights the distortion plane dominates — its cotangent is the constant lambda_dist / (H W) on
+    # every pixel, 1000x the photometric terms — so the scale is set by a high percentile (= that constant), and
+    # the few larger entries (d(D/alpha)/d(alpha) ~ 1/alpha^2 at nearly empty pixels) are winsorised there.
+    # What this config therefore stresses is the distortion gradient: differences of large terms per pixel and
+    # sign-mixed per-splat sums, where float32 atomics round relative to the terms rather than to the sum.
+    q = max(float(np.quantile(np.abs(np.concatenate([gc.ravel(), ga.ravel()])), 0.999)), 1e-30)
+    return np.clip(gc / q, -1.0, 1.0).astype(np.float32), np.clip(ga / q, -1.0, 1.0).astype(np.float32)
 
 
 def run_config(oracle, name, rows=None, regularizers=False):
@@ -94,7 +100,8 @@ def run_config(oracle, name, rows=None, regularizers=False):
     got = pipe.backward(gcb, gob)
     for k in ("dL_dmeans3D", "dL_dscales", "dL_drotations", "dL_dopacity", "dL_dshs", "dL_dmeans2D"):
         assert (got[k][~vis] == 0).all(), f"{k}: culled splats must have zero gradient"
-        two_bar_check(k, got[k], ref[k], ref64[k], _rel_grad, GRAD_TOL, GRAD_BUDGET_EXACT)
+        two_bar_check(k, got[k], ref[k], ref64[k], _rel_grad, GRAD_TOL, GRAD_BUDGET_EXACT,
+                      p999_bar=0.7 * GRAD_TOL if regularizers else None)
 
 
 def test_headline_full_frame(oracle, cuda_lib):
