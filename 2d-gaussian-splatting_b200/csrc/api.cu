@@ -227,6 +227,16 @@ int surfel_render_forward(const surfel_settings_t* s, uint32_t R, const void* ge
     p.out_color = out_color; p.out_others = out_others;
     p.out_plane = s->out_plane_stride > 0 ? (size_t)s->out_plane_stride : (size_t)f.W * f.H;
     if (p.out_plane < (size_t)f.W * f.H) { surfel_set_error("out_plane_stride smaller than the image"); return 1; }
+    p.rep_count = s->out_replica_count;
+    if (p.rep_count < 0 || p.rep_count > SURFEL_MAX_OUT_REPLICAS) { surfel_set_error("out_replica_count out of range"); return 1; }
+    if (p.rep_count > 0 && out_others != out_color + 3 * p.out_plane) {
+        surfel_set_error("out_replica_base needs out_others == out_color + 3 * out_plane_stride (one 10-plane frame)");
+        return 1;
+    }
+    for (int r = 0; r < SURFEL_MAX_OUT_REPLICAS; r++) {
+        p.rep_base[r] = r < p.rep_count ? (unsigned long long)s->out_replica_base[r] : 0ull;
+        if (r < p.rep_count && (p.rep_base[r] == 0 || (p.rep_base[r] & 3ull))) { surfel_set_error("out_replica_base: null or misaligned address"); return 1; }
+    }
     p.accum = (float*)((char*)image_ws + I.accum); p.n_contrib = (uint32_t*)((char*)image_ws + I.n_contrib);
     return launch_render_fwd(p, (cudaStream_t)stream);
 }

@@ -45,6 +45,8 @@ struct RenderParams {
     // backward
     const float* dL_dpix; const float* dL_dothers; float* grad_rec; int lowpass_quirk;
     size_t out_plane, grad_plane;   // floats between planes of the outputs / of the cotangents (default H*W)
+    // forward: replicated output frames (peer mappings or one multicast address), see surfel_settings
+    int rep_count; unsigned long long rep_base[8];
 };
 
 int launch_preprocess_fwd(const PreFwdParams& p, cudaStream_t stream);

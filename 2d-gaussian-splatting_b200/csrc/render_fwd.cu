@@ -146,16 +146,38 @@ __global__ void __launch_bounds__(256, SURFEL_FWD_BLOCKS) render_fwd_kernel(Rend
         p.accum[pix] = T; p.accum[HW + pix] = M1; p.accum[2 * HW + pix] = M2;
         p.n_contrib[pix] = last_contributor & 0x7FFFFFFFu; p.n_contrib[HW + pix] = median_contributor;
         const size_t OP = p.out_plane;
-        p.out_color[pix] = C0 + T * __ldg(p.bg + 0);
-        p.out_color[OP + pix] = C1 + T * __ldg(p.bg + 1);
-        p.out_color[2 * OP + pix] = C2 + T * __ldg(p.bg + 2);
-        p.out_others[kChDepth * OP + pix] = D;
-        p.out_others[kChAlpha * OP + pix] = 1.0f - T;
-        p.out_others[(kChNormal + 0) * OP + pix] = N0;
-        p.out_others[(kChNormal + 1) * OP + pix] = N1;
-        p.out_others[(kChNormal + 2) * OP + pix] = N2;
-        p.out_others[kChMidDepth * OP + pix] = median_depth;
-        p.out_others[kChDistortion * OP + pix] = dist;
+        const float c0 = C0 + T * __ldg(p.bg + 0), c1 = C1 + T * __ldg(p.bg + 1), c2 = C2 + T * __ldg(p.bg + 2);
+        if (p.rep_count == 0) {
+            p.out_color[pix] = c0;
+            p.out_color[OP + pix] = c1;
+            p.out_color[2 * OP + pix] = c2;
+            p.out_others[kChDepth * OP + pix] = D;
+            p.out_others[kChAlpha * OP + pix] = 1.0f - T;
+            p.out_others[(kChNormal + 0) * OP + pix] = N0;
+            p.out_others[(kChNormal + 1) * OP + pix] = N1;
+            p.out_others[(kChNormal + 2) * OP + pix] = N2;
+            p.out_others[kChMidDepth * OP + pix] = median_depth;
+            p.out_others[kChDistortion * OP + pix] = dist;
+        } else {
+            // Tile-band exchange fused into the producer: the band's pixels go straight to every replica of the
+            // frame — peer GPUs' memory over NVLink, or one NVSwitch multicast address that the switch fans out
+            // (a plain st.global to a multicast mapping IS multimem.st: same SASS) — fire-and-forget stores that
+            // overlap with the blending of the CTAs still running.  No all-gather follows; the caller runs a
+            // cross-GPU barrier before reading rows of other bands.
+            for (int r = 0; r < p.rep_count; r++) {
+                float* b = reinterpret_cast<float*>(p.rep_base[r]) + pix;
+                b[0] = c0;
+                b[OP] = c1;
+                b[2 * OP] = c2;
+                b[(3 + kChDepth) * OP] = D;
+                b[(3 + kChAlpha) * OP] = 1.0f - T;
+                b[(3 + kChNormal + 0) * OP] = N0;
+                b[(3 + kChNormal + 1) * OP] = N1;
+                b[(3 + kChNormal + 2) * OP] = N2;
+                b[(3 + kChMidDepth) * OP] = median_depth;
+                b[(3 + kChDistortion) * OP] = dist;
+            }
+        }
     }
 }
 

@@ -80,6 +80,10 @@ class GaussianRasterizationSettings(NamedTuple):
     # of one frame padded to equal bands, which an in-place all-gather then completes).
     tile_rows: Optional[Tuple[int, int]] = None
     out_buffers: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+    # out_replicas = device addresses (ints) of replicated 10-plane frames laid out like out_buffers (peer
+    # mappings of every GPU's frame, or one NVSwitch multicast address): the forward's output stores go to each of
+    # them instead of to out_buffers — the tile-band exchange fused into the render kernel (surfel_parallel).
+    out_replicas: Optional[Tuple[int, ...]] = None
 
 
 def _dev_f32(t, name, align=4):
@@ -99,7 +103,7 @@ def _ptr(t):
     return None if t is None or t.numel() == 0 else t.data_ptr()
 
 
-def _settings_struct(rs: GaussianRasterizationSettings, keep, out_plane=0, grad_plane=0):
+def _settings_struct(rs: GaussianRasterizationSettings, keep, out_plane=0, grad_plane=0, out_replicas=None):
     """ctypes view of the settings.  Built on every call: the reference's world_view_transform /
     full_proj_transform are transposed views, so contiguous copies are made here and must see the
     caller's current values (a long-lived GaussianRasterizer whose camera tensors are updated in place
@@ -110,11 +114,14 @@ def _settings_struct(rs: GaussianRasterizationSettings, keep, out_plane=0, grad_
     cp = _dev_f32(rs.campos, "campos")
     keep.extend([bg, vm, pm, cp])
     rows = rs.tile_rows if len(rs) > 12 and rs.tile_rows is not None else (0, 0)
+    reps = tuple(int(a) for a in (out_replicas or ()))
+    if len(reps) > 8:
+        raise RuntimeError("diff_surfel_rasterization: at most 8 output replicas")
     return _cabi.SurfelSettings(
         int(rs.image_height), int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy),
         float(rs.scale_modifier), int(rs.sh_degree), int(bool(rs.prefiltered)), int(bool(rs.debug)),
         int(rows[0]), int(rows[1]), bg.data_ptr(), vm.data_ptr(), pm.data_ptr(), cp.data_ptr(),
-        int(out_plane), int(grad_plane))
+        int(out_plane), int(grad_plane), len(reps), 0, (ctypes.c_uint64 * 8)(*reps))
 
 
 def _plane_stride(t, C, H, W):
@@ -198,7 +205,10 @@ class _RasterizeGaussians(torch.autograd.Function):
             if out_plane is None or _plane_stride(outb[1], 7, H, W) != out_plane or outb[0].device != dev:
                 raise RuntimeError("out_buffers must be float32 CUDA views of shape (3,H,W) and (7,H,W) with "
                                    "contiguous rows and one common plane stride")
-        cs = _settings_struct(rs, keep, out_plane=out_plane)
+        reps = rs.out_replicas if len(rs) > 14 else None
+        if reps and (outb is None or outb[1].data_ptr() != outb[0].data_ptr() + 12 * out_plane):
+            raise RuntimeError("out_replicas needs out_buffers that are the color / allmap planes of ONE 10-plane frame")
+        cs = _settings_struct(rs, keep, out_plane=out_plane, out_replicas=reps)
         means3D = _dev_f32(means3D, "means3D")
         opacities = _dev_f32(opacities, "opacities")
         sh = _dev_f32(sh, "shs", 16) if sh is not None and sh.numel() else None
@@ -271,7 +281,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         # context is a reference cycle — the frame (and everything else the context holds: workspaces, the
         # gradient bucket) would live until the cyclic garbage collector happens to run (measured: +1.8 GB of
         # reserved device memory and two cudaMalloc calls per config-5 step, profiles/r2_band_probe.md)
-        ctx.raster_settings = rs._replace(out_buffers=None) if outb is not None else rs
+        ctx.raster_settings = rs._replace(out_buffers=None, out_replicas=None) if outb is not None else rs
         ctx.num_rendered = cap        # the workspace layout was carved for `cap` instance slots
         ctx.M = M
         ctx.flags = (sh is not None, colors_precomp is not None, scales is not None, cov3Ds_precomp is not None)

@@ -23,6 +23,8 @@ class SurfelSettings(ctypes.Structure):
         ("tile_row_begin", ctypes.c_int32), ("tile_row_end", ctypes.c_int32),
         ("bg", c_void_p), ("viewmatrix", c_void_p), ("projmatrix", c_void_p), ("campos", c_void_p),
         ("out_plane_stride", ctypes.c_int64), ("grad_plane_stride", ctypes.c_int64),
+        ("out_replica_count", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("out_replica_base", ctypes.c_uint64 * 8),
     ]
 
 
@@ -102,7 +104,7 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError if the symbol is not exported
         fn.restype, fn.argtypes = res, args
-    if lib.surfel_abi_version() != 2:
+    if lib.surfel_abi_version() != 3:
         raise ImportError("libsurfel_b200.so ABI version mismatch")
     _lib = lib
     return lib

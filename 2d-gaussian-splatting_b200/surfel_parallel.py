@@ -141,7 +141,47 @@ def allgather_frame_inplace(buf: torch.Tensor, H: int, rank: int, world: int, gr
     return works
 
 
-_last = {"grad_bucket": None, "frame": None, "works": []}
+# ---------------------------------------------------------------------------------------------------
+# Exchange fused into the render kernel (gather="fused").
+#
+# The padded frame lives in SYMMETRIC memory (torch.distributed._symmetric_memory: every rank allocates the same
+# buffer and maps all peers' buffers over NVLink; with an NVSwitch the group also gets one multicast address
+# whose stores the switch fans out to every GPU).  The op is handed those addresses (`out_replicas`) and its
+# render kernel stores each output pixel of the band to every replica — the all-gather is done by the stores of
+# the kernel that produces the data, overlapped with the blending of the CTAs still running, and the only
+# collective left is a cross-GPU barrier (`handle.barrier`) before anyone reads rows outside its own band.
+# Frames come from a ring of two symmetric buffers per (shape, group): a rank can only start overwriting a
+# buffer after the barrier of the NEXT frame, which every rank enters after the work it queued on the previous
+# contents (same stream).  Outputs are therefore views that stay valid until the second-next fused call.
+# ---------------------------------------------------------------------------------------------------
+_sym_frames = {}
+
+
+def symmetric_frame(H: int, W: int, world: int, device, group=None, multicast: bool = False):
+    """(frame (10, H_pad, W), replica addresses, handle) — the next buffer of the ring for this shape."""
+    import torch.distributed._symmetric_memory as symm
+    g = group if group is not None else dist.group.WORLD
+    key = (H, W, world, torch.device(device).index, g.group_name)
+    ent = _sym_frames.get(key)
+    if ent is None:
+        bufs, hdls = [], []
+        for _ in range(2):
+            t = symm.empty((10, equal_band_rows(H, world) * world * TILE, W), dtype=torch.float32, device=device)
+            hdls.append(symm.rendezvous(t, g))
+            bufs.append(t)
+        ent = _sym_frames[key] = {"bufs": bufs, "hdls": hdls, "turn": 0}
+    i = ent["turn"]
+    ent["turn"] ^= 1
+    buf, hdl = ent["bufs"][i], ent["hdls"][i]
+    off = buf.data_ptr() - int(hdl.buffer_ptrs[hdl.rank])       # the tensor's offset inside the symmetric allocation
+    if off < 0 or off + buf.numel() * 4 > int(hdl.buffer_size):
+        raise RuntimeError("symmetric frame is not inside this rank's symmetric allocation")
+    mc = int(hdl.multicast_ptr) if multicast and hdl.has_multicast_support else 0
+    reps = (mc + off,) if mc else tuple(int(a) + off for a in hdl.buffer_ptrs)
+    return buf, reps, hdl
+
+
+_last = {"grad_bucket": None, "frame": None, "works": [], "fused_via": None}
 
 
 def last_exchange_buffers():
@@ -160,19 +200,33 @@ class _BandFrame(torch.autograd.Function):
         from diff_surfel_rasterization import _RasterizeGaussians, _mark
         H, W = int(settings.image_height), int(settings.image_width)
         _mark("band_enter")
-        buf = padded_frame(10, H, W, world, means3D.device)
-        _mark("band_frame_allocated")
         band = equal_band(H, rank, world)
-        rs = settings._replace(tile_rows=band, out_buffers=(buf[:3, :H], buf[3:, :H]))
+        fused = gather in ("fused", "fused_multicast") and world > 1 and dist.is_initialized()
+        if fused:
+            buf, reps, hdl = symmetric_frame(H, W, world, means3D.device, group, multicast=(gather == "fused_multicast"))
+            if gather == "fused_multicast" and len(reps) != 1:
+                raise RuntimeError("gather='fused_multicast': this process group has no multicast address (no NVSwitch?)")
+            _last["fused_via"] = "multicast" if len(reps) == 1 else "peer stores"
+            rs = settings._replace(tile_rows=band, out_buffers=(buf[:3, :H], buf[3:, :H]), out_replicas=reps)
+        else:
+            buf = padded_frame(10, H, W, world, means3D.device)
+            rs = settings._replace(tile_rows=band, out_buffers=(buf[:3, :H], buf[3:, :H]))
+        _mark("band_frame_allocated")
         color, radii, allmap = _RasterizeGaussians.forward(ctx, means3D, means2D, sh, colors_precomp, opacities,
                                                            scales, rotations, cov3Ds_precomp, rs)
-        _last["works"] = allgather_frame_inplace(buf, H, rank, world, group, async_op=(gather == "async"))
-        _mark("band_gather_enqueued")
-        _last["frame"] = buf
         if world > 1 and dist.is_initialized():
             # radii (and so visibility_filter / max_radii2D downstream) are per-band partials: a splat's tile
-            # rect is clipped to the band before it is counted
+            # rect is clipped to the band before it is counted.  Reduced BEFORE the frame exchange is enqueued: the
+            # backend runs its collectives in order, so a blocking collective queued behind asynchronous gathers
+            # would make the current stream wait for them (measured: no overlap at all in the first async version).
             dist.all_reduce(radii, op=dist.ReduceOp.MAX, group=group)
+        if fused:
+            hdl.barrier(channel=0)          # every rank's band has landed in every replica
+            _last["works"] = []
+        else:
+            _last["works"] = allgather_frame_inplace(buf, H, rank, world, group, async_op=(gather == "async"))
+        _mark("band_gather_enqueued")
+        _last["frame"] = buf
         _mark("band_exit")
         ctx.band_meta = (world, group, grad_reduce)
         return color, radii, allmap
@@ -200,12 +254,19 @@ def rasterize_tile_band(rasterizer_cls, settings, rank: int, world: int, group=N
     the current stream at once, the other ranks' rows after result["wait"]() — so a loss that is local to the
     band (per-pixel terms; SSIM with a 5-row halo inside the band) can run its backward, which reads nothing
     but this band's cotangent rows, while the exchange is still in flight.
+
+    gather="fused" has no all-gather at all: the frame lives in symmetric memory and the render kernel itself
+    stores the band's pixels into every GPU's copy over NVLink (one store per peer and value; measured at N = 2:
+    forward + exchange 3.1 ms against 3.9 ms for forward + NCCL all-gather); a cross-GPU barrier follows.
+    "fused_multicast" sends ONE store per value to the group's NVSwitch multicast address instead (measured
+    slower at N = 2 — 7.6 ms — the switch handles 32-byte multicast writes poorly; kept for comparison).  The
+    returned views belong to a ring of two frames and stay valid until the second-next fused call.
     `rasterizer_cls` is accepted for symmetry with the single-GPU call and is not used."""
     del rasterizer_cls
     if grad_reduce not in ("all_reduce", "none"):
         raise ValueError("grad_reduce must be 'all_reduce' or 'none'")
-    if gather not in ("sync", "async"):
-        raise ValueError("gather must be 'sync' or 'async'")
+    if gather not in ("sync", "async", "fused", "fused_multicast"):
+        raise ValueError("gather must be 'sync', 'async', 'fused' or 'fused_multicast'")
     empty = torch.Tensor([])
     g = lambda k: inputs.get(k) if inputs.get(k) is not None else empty
     if (inputs.get("shs") is None) == (inputs.get("colors_precomp") is None):

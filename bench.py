@@ -304,27 +304,41 @@ def tile_band_leg(rank, world, dev, steps=6, warmup=2, workload="config5"):
                 acc[i] += ev[a].elapsed_time(ev[b])
         return res
 
-    def step_overlapped(reduce):
-        """The same frame with the exchange taken off the critical path: the all-gathers are only enqueued, the band
-        backward (which reads this band's cotangent rows only) runs while they are in flight, then the gradient
-        reduction.  What a band-local loss permits; the full frame is complete at the end of the step."""
-        for t in list(leaf.values()) + [m2d]:
-            t.grad = None
-        ev[0].record()
-        res = SP.rasterize_tile_band(GaussianRasterizer, rs, rank, world, grad_reduce="none", gather="async",
-                                     means3D=leaf["means3D"], means2D=m2d, shs=leaf["shs"], opacities=leaf["opacities"],
-                                     scales=leaf["scales"], rotations=leaf["rotations"])
-        torch.autograd.backward([res["render"], res["allmap"]], [gc, go])
-        _, bucket = SP.last_exchange_buffers()
+    shard_buf = {}
+
+    def reduce_grads(bucket, reduce):
         if reduce == "all_reduce":
             dist.all_reduce(bucket)
         else:
-            dist.reduce_scatter_tensor(torch.empty(bucket.numel() // world, device=dev), bucket)
-        res["wait"]()                                                        # the frame is complete on this stream
+            if "t" not in shard_buf:
+                shard_buf["t"] = torch.empty(bucket.numel() // world, device=dev)
+            dist.reduce_scatter_tensor(shard_buf["t"], bucket)
+
+    def step_variant(gather, reduce, acc_key):
+        """The same frame with the exchange taken off the critical path.
+        gather="async": the all-gathers are only enqueued and the band backward (which reads this band's cotangent
+        rows only) runs while they are in flight — what a band-local loss permits.
+        gather="fused"/"fused_p2p": no all-gather at all; the render kernel stores the band into every GPU's copy of
+        the frame (NVSwitch multicast / peer stores over NVLink) and a cross-GPU barrier follows.
+        Either way the full frame is complete, and the gradients reduced, at the end of the timed region."""
+        for t in list(leaf.values()) + [m2d]:
+            t.grad = None
+        ev[0].record()
+        res = SP.rasterize_tile_band(GaussianRasterizer, rs, rank, world, grad_reduce="none", gather=gather,
+                                     means3D=leaf["means3D"], means2D=m2d, shs=leaf["shs"], opacities=leaf["opacities"],
+                                     scales=leaf["scales"], rotations=leaf["rotations"])
         ev[1].record()
+        torch.autograd.backward([res["render"], res["allmap"]], [gc, go])
+        _, bucket = SP.last_exchange_buffers()
+        reduce_grads(bucket, reduce)
+        res["wait"]()                                                        # the frame is complete on this stream
+        ev[2].record()
         torch.cuda.synchronize()
-        acc_ov[reduce] += ev[0].elapsed_time(ev[1])
+        acc_var[acc_key] = acc_var.get(acc_key, 0.0) + ev[0].elapsed_time(ev[2])
+        acc_var[acc_key + ":fwd"] = acc_var.get(acc_key + ":fwd", 0.0) + ev[0].elapsed_time(ev[1])
         return res
+
+    acc_var = {}
 
     import ctypes
     import time as _time
@@ -343,23 +357,43 @@ def tile_band_leg(rank, world, dev, steps=6, warmup=2, workload="config5"):
     lib.surfel_profile_enable(0); lib.surfel_profile_read(ms_arr, cnt_arr)
     kernels = {lib.surfel_profile_stage_name(i).decode(): round(ms_arr[i] / steps, 3) for i in range(nst) if cnt_arr[i]}
     bucket_divisible = SP.last_exchange_buffers()[1].numel() % world == 0
-    for mode in ("all_reduce",) + (("reduce_scatter",) if bucket_divisible else ()):
-        step_overlapped(mode); acc_ov[mode] = 0.0                            # one untimed step per mode
-        dist.barrier(); torch.cuda.synchronize()
-        for _ in range(steps):
-            res_ov = step_overlapped(mode)
-    tt = torch.tensor([a / steps for a in acc] + [acc_ov["all_reduce"] / steps, acc_ov["reduce_scatter"] / steps],
-                      device=dev, dtype=torch.float64)
+    variants = [("async", "all_reduce", "overlapped"), ("fused", "all_reduce", "fused"), ("fused_multicast", "all_reduce", "fused_multicast")]
+    if bucket_divisible:
+        variants.append(("fused", "reduce_scatter", "fused_rs"))
+    var_ms, var_err, var_res, fused_via = {}, {}, {}, {}
+    for gather, reduce, key in variants:
+        try:
+            step_variant(gather, reduce, key)                                # one untimed step per variant
+            acc_var.pop(key, None); acc_var.pop(key + ":fwd", None)
+            dist.barrier(); torch.cuda.synchronize()
+            for _ in range(steps):
+                var_res[key] = step_variant(gather, reduce, key)
+            fused_via[key] = SP._last.get("fused_via") if gather.startswith("fused") else None
+            tv = torch.tensor([acc_var[key] / steps, acc_var[key + ":fwd"] / steps], device=dev, dtype=torch.float64)
+            dist.all_reduce(tv, op=dist.ReduceOp.MAX)
+            var_ms[key] = (float(tv[0]), float(tv[1]))
+        except Exception as ex:     # noqa: BLE001 — e.g. no symmetric memory / multicast on this box: reported, not hidden
+            var_err[key] = f"{type(ex).__name__}: {ex}"[:300]
+    tt = torch.tensor([a / steps for a in acc], device=dev, dtype=torch.float64)
     dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    fwd_total, bwd, allreduce, gather, rscatter, frame, frame_ov, frame_ov_rs = (float(x) for x in tt)
+    fwd_total, bwd, allreduce, gather, rscatter, frame = (float(x) for x in tt)
     out = {"workload": f"{workload}: {P} surfels, one {W}x{H} frame in {world} tile-row bands",
            "ms_frame": frame, "ms_band_fwd": max(0.0, fwd_total - gather), "ms_allgather": gather, "ms_band_bwd": bwd,
            "ms_allreduce": allreduce, "ms_reduce_scatter_alternative": rscatter,
            "gather_bytes_per_rank": int(10 * 4 * W * SP.equal_band_rows(H, world) * 16),
            "grad_bytes": int(SP.last_exchange_buffers()[1].numel() * 4),
-           "ms_frame_overlapped": frame_ov, "ms_frame_overlapped_reduce_scatter": frame_ov_rs if bucket_divisible else None,
+           "ms_frame_overlapped": var_ms.get("overlapped", (None,))[0],
            "overlapped": "all-gathers enqueued asynchronously and hidden behind the band backward (band-local cotangents), "
                          "then the gradient all-reduce / reduce-scatter; full frame complete at the end of the step",
+           "ms_frame_fused": var_ms.get("fused", (None,))[0], "ms_band_fwd_fused": var_ms.get("fused", (None, None))[1],
+           "ms_frame_fused_reduce_scatter": var_ms.get("fused_rs", (None,))[0],
+           "ms_frame_fused_multicast": var_ms.get("fused_multicast", (None,))[0],
+           "ms_band_fwd_fused_multicast": var_ms.get("fused_multicast", (None, None))[1],
+           "fused": "no all-gather: the render kernel stores its band into every GPU's copy of the frame in symmetric "
+                    "memory over NVLink (one store per peer and value; fused_multicast = one store per value to the "
+                    "NVSwitch multicast address), then a cross-GPU barrier; ms_band_fwd_fused = band forward + exchange + "
+                    "barrier, to compare with ms_band_fwd + ms_allgather",
+           "variant_errors": var_err or None,
            "Msplats_per_s": P / frame / 1e3, "steps": steps, "kernel_ms_rank0": kernels, "host_ms_per_step_rank0": t_host,
            "how": "padded frame, bands rendered in place, one in-place all_gather_into_tensor per plane; cotangents read in "
                   "place; one all_reduce of the flat gradient bucket (reduce-scatter timed as the sharded-optimizer alternative)"}
@@ -370,7 +404,9 @@ def tile_band_leg(rank, world, dev, steps=6, warmup=2, workload="config5"):
                                                           opacities=leaf["opacities"], scales=leaf["scales"], rotations=leaf["rotations"])
         out["stitched_equals_single_gpu"] = bool(torch.equal(res["render"], color) and torch.equal(res["allmap"], allmap)
                                                  and torch.equal(res["radii"], radii)
-                                                 and torch.equal(res_ov["render"], color) and torch.equal(res_ov["allmap"], allmap))
+                                                 and all(torch.equal(r["render"], color) and torch.equal(r["allmap"], allmap)
+                                                         for r in var_res.values()))
+        out["variants_checked"] = sorted(var_res)
     dist.barrier()
     return out
 

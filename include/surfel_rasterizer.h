@@ -46,7 +46,8 @@
 extern "C" {
 #endif
 
-#define SURFEL_ABI_VERSION 2
+#define SURFEL_ABI_VERSION 3
+#define SURFEL_MAX_OUT_REPLICAS 8
 
 /* Mirrors GaussianRasterizationSettings (fields constructed at
  * /root/reference/gaussian_renderer/__init__.py:37-51) plus the tile-row band used by the
@@ -72,6 +73,18 @@ typedef struct surfel_settings {
      * equal bands, which an in-place all-gather then completes — no staging or stitch copies. */
     int64_t out_plane_stride;
     int64_t grad_plane_stride;
+    /* Forward outputs written to REPLICATED frames (multi-GPU tile-band mode): when
+     * out_replica_count > 0 the render kernel stores every output value of its band to each address
+     * out_replica_base[r] + 4 * (plane * out_plane_stride + y * W + x), plane = 0..2 for out_color and 3..9 for
+     * out_others, INSTEAD of to out_color / out_others (which must still be valid pointers laid out the same way:
+     * out_others == out_color + 3 * out_plane_stride).  The addresses are device pointers valid in this process:
+     * peer mappings of the other GPUs' frames and this GPU's own frame (symmetric memory over NVLink), or ONE
+     * NVSwitch multicast address that fans a single store out to all of them.  The exchange of the band outputs
+     * is thereby done by the stores of the kernel that produces them; the caller only has to run a cross-GPU
+     * barrier before any rank reads rows outside its own band.  0 = off (default). */
+    int32_t out_replica_count;
+    int32_t reserved0;
+    uint64_t out_replica_base[SURFEL_MAX_OUT_REPLICAS];
 } surfel_settings_t;
 
 int surfel_abi_version(void);

@@ -39,6 +39,16 @@ def _worker(rank, world, port, out):
         gc, go = S.make_cotangents(W, H, 31)
         ((res["render"] * gc.to(dev)).sum() + (res["allmap"] * go.to(dev)).sum()).backward()
         grads = [leaf[k].grad for k in ("means3D", "scales", "rotations", "opacities", "shs")]   # already summed over the ranks
+        # the same frame with the exchange done by the render kernel's own stores (symmetric memory: NVSwitch
+        # multicast if the group has it, and peer stores), and with asynchronous gathers
+        variants = {}
+        for mode in ("fused", "fused_multicast", "async"):
+            with torch.no_grad():
+                rv = SP.rasterize_tile_band(GaussianRasterizer, rs, rank, world, gather=mode, means3D=leaf["means3D"], means2D=m2d,
+                                            shs=leaf["shs"], opacities=leaf["opacities"], scales=leaf["scales"],
+                                            rotations=leaf["rotations"])
+            rv["wait"]()
+            variants[mode] = (rv["render"].clone(), rv["allmap"].clone(), SP._last.get("fused_via"))
         if rank == 0:
             # single-GPU reference on the same device
             leaf2 = {k: v.to(dev).requires_grad_(True) for k, v in scene.items()}
@@ -51,7 +61,8 @@ def _worker(rank, world, port, out):
             for k, g in zip(("means3D", "scales", "rotations", "opacities", "shs"), grads):
                 ref = leaf2[k].grad
                 errs[k] = float((g - ref).abs().max() / (ref.abs().max() + 1e-30))
-            torch.save({"ok_img": ok_img, "errs": errs}, out)
+            ok_var = {m: bool(torch.equal(v[0], color) and torch.equal(v[1], allmap)) for m, v in variants.items()}
+            torch.save({"ok_img": ok_img, "errs": errs, "ok_var": ok_var, "via": {m: v[2] for m, v in variants.items()}}, out)
     finally:
         dist.destroy_process_group()
 
@@ -68,3 +79,5 @@ def test_tile_band_two_gpus(tmp_path):
     r = torch.load(out)
     assert r["ok_img"], "the frame completed in place (or the MAX-reduced radii) differs from the single-GPU result"
     assert max(r["errs"].values()) < 1e-3, r["errs"]
+    print("exchange variants:", r["ok_var"], r["via"])
+    assert all(r["ok_var"].values()), f"a frame completed by a fused / asynchronous exchange differs from the single-GPU result: {r['ok_var']}"
