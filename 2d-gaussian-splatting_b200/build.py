@@ -70,8 +70,12 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or not os.path.exists(LIB):
-        cmd = [_nvcc()] + ARCH + ["-shared", "-o", LIB] + objs + ["-lcudart"]
+        # link next to the target and rename: a reader (a process loading the library, a snapshot of the tree)
+        # never sees a half-written file
+        tmp = LIB + ".link"
+        cmd = [_nvcc()] + ARCH + ["-shared", "-o", tmp] + objs + ["-lcudart"]
         subprocess.check_call(cmd)
+        os.replace(tmp, LIB)
     return LIB
 
 

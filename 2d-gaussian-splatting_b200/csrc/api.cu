@@ -314,7 +314,17 @@ int surfel_backward(const surfel_settings_t* s, int P, int M, uint32_t R, const 
     q.dL_dmeans2D = dL_dmeans2D; q.dL_dcolors = dL_dcolors; q.dL_dopacity = dL_dopacity;
     q.dL_dmeans3D = dL_dmeans3D; q.dL_dtransMat = dL_dtransMat; q.dL_dsh = dL_dsh;
     q.dL_dscales = dL_dscales; q.dL_drots = dL_drotations;
+    q.defer_sh = (s->sh_grad_deferred && shs != nullptr && !has_colors_precomp) ? 1 : 0;
+    if (q.defer_sh && !dL_dcolors) { surfel_set_error("sh_grad_deferred needs dL_dcolors"); return 1; }
     return launch_preprocess_bwd(q, st);
+}
+
+int surfel_sh_grad_expand(int P, int M, int sh_degree, const float* means3D, const float* campos,
+                          const float* dL_dcolors, float* dL_dsh, void* stream) {
+    if (P <= 0 || M <= 0) return 0;
+    if (!means3D || !campos || !dL_dcolors || !dL_dsh) { surfel_set_error("surfel_sh_grad_expand: NULL argument"); return 1; }
+    if (sh_degree < 0 || sh_degree > 3 || (sh_degree + 1) * (sh_degree + 1) > M) { surfel_set_error("surfel_sh_grad_expand: degree / M mismatch"); return 1; }
+    return launch_sh_grad_expand(P, M, sh_degree, means3D, campos, dL_dcolors, dL_dsh, (cudaStream_t)stream);
 }
 
 int surfel_mark_visible(int P, const float* means3D, const float* viewmatrix,

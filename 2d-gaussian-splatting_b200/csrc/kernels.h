@@ -34,6 +34,7 @@ struct PreBwdParams {
     float* dL_dsh;                    // (P,M,3) out
     float* dL_dscales;                // (P,2) out
     float* dL_drots;                  // (P,4) out
+    int defer_sh;                     // 1: dL_dsh is NOT written; dL_dcolors receives the clamp-masked colour gradient
 };
 
 struct RenderParams {
@@ -53,6 +54,10 @@ int launch_preprocess_fwd(const PreFwdParams& p, cudaStream_t stream);
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
                         cudaStream_t stream);
 int launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t stream);
+// dL_dsh (P,M,3) = SH basis(direction of the splat) (x) dL_dcolors (P,3): the rank-1 expansion that
+// preprocess_bwd skips in defer_sh mode (so that a multi-GPU caller can reduce 3 floats per splat instead of 3M)
+int launch_sh_grad_expand(int P, int M, int D, const float* means3D, const float* campos,
+                          const float* dL_dcolors, float* dL_dsh, cudaStream_t stream);
 
 // binning
 int launch_duplicate_with_keys(int P, int gx, int gy, int row0, int row1, const float4* tmat,

@@ -52,6 +52,8 @@ __global__ void __launch_bounds__(128, 6) preprocess_bwd_kernel(PreBwdParams p) 
     float tm[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     float g3[3] = {0, 0, 0}, gs[2] = {0, 0}, gq[4] = {0, 0, 0, 0};
     float px = 0, py = 0, pz = 0, proxy2 = 0, proxy5 = 0;
+    float dR_out[3] = {0, 0, 0};      // clamp-masked colour gradient (what the SH expansion multiplies)
+    const bool emit_sh = !p.defer_sh;
 
     // Every input of the splat is requested in the first round trip to HBM: the SH rows by cp.async
     // (LDGSTS) straight into the warp's panel, position / rotation / scale into registers, while the
@@ -211,6 +213,7 @@ __global__ void __launch_bounds__(128, 6) preprocess_bwd_kernel(PreBwdParams p) 
         if (visible) {
             const uint8_t cb = p.clamped[idx];
             const float dR[3] = {(cb & 1) ? 0.0f : gc[0], (cb & 2) ? 0.0f : gc[1], (cb & 4) ? 0.0f : gc[2]};
+            dR_out[0] = dR[0]; dR_out[1] = dR[1]; dR_out[2] = dR[2];
             const float dox = px - p.campos[0], doy = py - p.campos[1], doz = pz - p.campos[2];
             const float sq = dox * dox + doy * doy + doz * doz;
             const float invl = 1.0f / sqrtf(sq);
@@ -218,7 +221,7 @@ __global__ void __launch_bounds__(128, 6) preprocess_bwd_kernel(PreBwdParams p) 
             float ddx = 0, ddy = 0, ddz = 0;
 #define SHV(i, c) (kStaged ? v[3 * (i) + (c)] : shg[3 * (i) + (c)])
 #define GS(i, val) do { const float _v = (val); if (kStaged) { v[3 * (i)] = _v * dR[0]; v[3 * (i) + 1] = _v * dR[1]; v[3 * (i) + 2] = _v * dR[2]; } \
-                        else { gsh[3 * (i)] = _v * dR[0]; gsh[3 * (i) + 1] = _v * dR[1]; gsh[3 * (i) + 2] = _v * dR[2]; } } while (0)
+                        else if (emit_sh) { gsh[3 * (i)] = _v * dR[0]; gsh[3 * (i) + 1] = _v * dR[1]; gsh[3 * (i) + 2] = _v * dR[2]; } } while (0)
 #define DOT(i) (dR[0] * SHV(i, 0) + dR[1] * SHV(i, 1) + dR[2] * SHV(i, 2))
             // every DOT(i) is taken before GS(i) overwrites coefficient i (in-place row)
             GS(0, SH_C0);
@@ -261,7 +264,10 @@ __global__ void __launch_bounds__(128, 6) preprocess_bwd_kernel(PreBwdParams p) 
             g3[1] += (-dox * doy * ddx + (dox * dox + doz * doz) * ddy - doz * doy * ddz) * inv3;
             g3[2] += (-dox * doz * ddx - doy * doz * ddy + (dox * dox + doy * doy) * ddz) * inv3;
         }
-        if (kStaged) {
+        if (!emit_sh) {
+            // deferred: the caller expands basis (x) colour gradient itself (surfel_sh_grad_expand), typically
+            // after summing the 3-float colour gradients of several GPUs
+        } else if (kStaged) {
             // row back to shared memory (zeros for culled splats and for coefficients beyond the
             // active degree), then one coalesced sweep to HBM
 #pragma unroll
@@ -291,7 +297,11 @@ __global__ void __launch_bounds__(128, 6) preprocess_bwd_kernel(PreBwdParams p) 
     o[2] = 0.0f;
     p.dL_dopacity[idx] = gopa;
     o = p.dL_dmeans3D + 3 * (size_t)idx; o[0] = g3[0]; o[1] = g3[1]; o[2] = g3[2];
-    if (p.dL_dcolors) { o = p.dL_dcolors + 3 * (size_t)idx; o[0] = gc[0]; o[1] = gc[1]; o[2] = gc[2]; }
+    if (p.dL_dcolors) {
+        o = p.dL_dcolors + 3 * (size_t)idx;
+        if (p.defer_sh) { o[0] = dR_out[0]; o[1] = dR_out[1]; o[2] = dR_out[2]; }
+        else            { o[0] = gc[0]; o[1] = gc[1]; o[2] = gc[2]; }
+    }
     if (p.dL_dtransMat) {
         o = p.dL_dtransMat + 9 * (size_t)idx;
 #pragma unroll
@@ -301,11 +311,72 @@ __global__ void __launch_bounds__(128, 6) preprocess_bwd_kernel(PreBwdParams p) 
     if (p.dL_drots) { o = p.dL_drots + 4 * (size_t)idx; o[0] = gq[0]; o[1] = gq[1]; o[2] = gq[2]; o[3] = gq[3]; }
 }
 
+// One warp per 32 splats: every lane evaluates the real SH basis of its own splat's view direction into shared
+// memory (the same expressions as the GS(...) lines above), then the warp writes the 32 rows of 3M floats with
+// coalesced stores, each value = basis[k] * dL_dcolor[c].  Splats whose colour gradient is exactly zero (culled
+// everywhere) get zero rows without touching their direction.
+__global__ void __launch_bounds__(128) sh_grad_expand_kernel(int P, int M, int D, const float* __restrict__ means3D,
+                                                             const float* __restrict__ campos,
+                                                             const float* __restrict__ dcol, float* __restrict__ dsh) {
+    __shared__ float s_b[4][32][21];            // 16 basis values + 3 colour gradients per splat; odd stride: conflict-free
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int first = (blockIdx.x * 4 + warp) * 32;
+    if (first >= P) return;
+    const int idx = first + lane;
+    float b[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) b[k] = 0.0f;
+    float c0 = 0, c1 = 0, c2 = 0;
+    if (idx < P) { c0 = dcol[3 * (size_t)idx]; c1 = dcol[3 * (size_t)idx + 1]; c2 = dcol[3 * (size_t)idx + 2]; }
+    if (c0 != 0.0f || c1 != 0.0f || c2 != 0.0f) {
+        const float dox = means3D[3 * (size_t)idx] - campos[0], doy = means3D[3 * (size_t)idx + 1] - campos[1],
+                    doz = means3D[3 * (size_t)idx + 2] - campos[2];
+        const float invl = 1.0f / sqrtf(dox * dox + doy * doy + doz * doz);
+        const float x = dox * invl, y = doy * invl, z = doz * invl;
+        b[0] = SH_C0;
+        if (D > 0) {
+            b[1] = -SH_C1 * y; b[2] = SH_C1 * z; b[3] = -SH_C1 * x;
+            if (D > 1) {
+                const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+                b[4] = b_SH_C2[0] * xy; b[5] = b_SH_C2[1] * yz; b[6] = b_SH_C2[2] * (2.0f * zz - xx - yy);
+                b[7] = b_SH_C2[3] * xz; b[8] = b_SH_C2[4] * (xx - yy);
+                if (D > 2) {
+                    b[9] = b_SH_C3[0] * y * (3.0f * xx - yy); b[10] = b_SH_C3[1] * xy * z;
+                    b[11] = b_SH_C3[2] * y * (4.0f * zz - xx - yy);
+                    b[12] = b_SH_C3[3] * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+                    b[13] = b_SH_C3[4] * x * (4.0f * zz - xx - yy); b[14] = b_SH_C3[5] * z * (xx - yy);
+                    b[15] = b_SH_C3[6] * x * (xx - 3.0f * yy);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; k++) s_b[warp][lane][k] = b[k];
+    s_b[warp][lane][16] = c0; s_b[warp][lane][17] = c1; s_b[warp][lane][18] = c2;
+    __syncwarp();
+    const int rows = min(32, P - first), row_len = 3 * M;
+    float* out = dsh + (size_t)first * row_len;
+    for (int f = lane; f < rows * row_len; f += 32) {
+        const int row = f / row_len, j = f - row * row_len;
+        const int k = j / 3, c = j - 3 * k;
+        out[f] = k < 16 ? s_b[warp][row][k] * s_b[warp][row][16 + c] : 0.0f;
+    }
+}
+
+int launch_sh_grad_expand(int P, int M, int D, const float* means3D, const float* campos,
+                          const float* dL_dcolors, float* dL_dsh, cudaStream_t stream) {
+    if (P <= 0 || M <= 0) return 0;
+    sh_grad_expand_kernel<<<(P + 127) / 128, 128, 0, stream>>>(P, M, D, means3D, campos, dL_dcolors, dL_dsh);
+    SURFEL_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int launch_preprocess_bwd(const PreBwdParams& p, cudaStream_t stream) {
     if (p.P <= 0) return 0;
     LaunchScope scope(kStPreBwd, stream);
     const bool staged = !p.has_colors_precomp && p.shs != nullptr && p.D <= 3 && p.M == 16 &&
-                        reinterpret_cast<uintptr_t>(p.shs) % 16 == 0 && reinterpret_cast<uintptr_t>(p.dL_dsh) % 16 == 0;
+                        reinterpret_cast<uintptr_t>(p.shs) % 16 == 0 &&
+                        (p.defer_sh || reinterpret_cast<uintptr_t>(p.dL_dsh) % 16 == 0);
     if (staged) preprocess_bwd_kernel<true><<<(p.P + 127) / 128, 128, 0, stream>>>(p);
     else        preprocess_bwd_kernel<false><<<(p.P + 127) / 128, 128, 0, stream>>>(p);
     SURFEL_CUDA_OK(cudaGetLastError());

@@ -103,7 +103,7 @@ def _ptr(t):
     return None if t is None or t.numel() == 0 else t.data_ptr()
 
 
-def _settings_struct(rs: GaussianRasterizationSettings, keep, out_plane=0, grad_plane=0, out_replicas=None):
+def _settings_struct(rs: GaussianRasterizationSettings, keep, out_plane=0, grad_plane=0, out_replicas=None, defer_sh=False):
     """ctypes view of the settings.  Built on every call: the reference's world_view_transform /
     full_proj_transform are transposed views, so contiguous copies are made here and must see the
     caller's current values (a long-lived GaussianRasterizer whose camera tensors are updated in place
@@ -121,7 +121,7 @@ def _settings_struct(rs: GaussianRasterizationSettings, keep, out_plane=0, grad_
         int(rs.image_height), int(rs.image_width), float(rs.tanfovx), float(rs.tanfovy),
         float(rs.scale_modifier), int(rs.sh_degree), int(bool(rs.prefiltered)), int(bool(rs.debug)),
         int(rows[0]), int(rows[1]), bg.data_ptr(), vm.data_ptr(), pm.data_ptr(), cp.data_ptr(),
-        int(out_plane), int(grad_plane), len(reps), 0, (ctypes.c_uint64 * 8)(*reps))
+        int(out_plane), int(grad_plane), len(reps), int(bool(defer_sh)), (ctypes.c_uint64 * 8)(*reps))
 
 
 def _plane_stride(t, C, H, W):
@@ -159,13 +159,16 @@ def _pinned_u32(device):
     return ent
 
 
-def _grad_buffers(lib, dev, P, M, has_sh, has_colors, has_scales, has_cov):
+def _grad_buffers(lib, dev, P, M, has_sh, has_colors, has_scales, has_cov, defer_sh=False):
     """Every gradient the backward writes, carved out of ONE flat allocation (offsets are multiples of four
     floats, so the 128-bit stores of the kernels stay aligned): a caller that has to reduce the gradients
     across ranks (surfel_parallel) reduces `bucket` in place instead of concatenating eight tensors."""
+    # defer_sh (multi-GPU band mode): the bucket carries the 3-float colour gradient instead of the (M,3) SH
+    # gradient, which is its rank-1 expansion and is produced AFTER the bucket has been reduced across ranks
+    defer_sh = bool(defer_sh and has_sh)
     parts = [("d_means3D", (P, 3), True), ("d_means2D", (P, 3), True), ("d_opacity", (P, 1), True),
-             ("d_sh", (P, M, 3), has_sh), ("d_scales", (P, 2), has_scales), ("d_rot", (P, 4), has_scales),
-             ("d_colors", (P, 3), has_colors), ("d_cov", (P, 9), has_cov)]
+             ("d_sh", (P, M, 3), has_sh and not defer_sh), ("d_scales", (P, 2), has_scales), ("d_rot", (P, 4), has_scales),
+             ("d_colors", (P, 3), has_colors or defer_sh), ("d_cov", (P, 9), has_cov)]
     off, plan = 0, []
     for name, shape, on in parts:
         n = 1
@@ -179,6 +182,9 @@ def _grad_buffers(lib, dev, P, M, has_sh, has_colors, has_scales, has_cov):
     for name, shape, o, n in plan:
         out[name] = bucket[o:o + n].view(shape)
     out["bucket"] = bucket
+    if defer_sh:
+        out["d_sh"] = torch.empty((P, M, 3), dtype=torch.float32, device=dev)
+    out["defer_sh"] = defer_sh
     out["scratch"] = torch.empty((max(P, 1), lib.surfel_grad_scratch_floats()), dtype=torch.float32, device=dev)
     return out
 
@@ -257,7 +263,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                 # must land before the queued forward kernels drain) is as short as possible.
                 if any(ctx.needs_input_grad[:8]):
                     ctx.bwd_bufs = _grad_buffers(lib, dev, P, M, sh is not None, colors_precomp is not None,
-                                                 scales is not None, cov3Ds_precomp is not None)
+                                                 scales is not None, cov3Ds_precomp is not None,
+                                                 defer_sh=getattr(ctx, "defer_sh", False))
                 _mark("speculative_work_launched")
                 ev.synchronize()
                 _mark("R_known")
@@ -318,13 +325,24 @@ class _RasterizeGaussians(torch.autograd.Function):
             g_color, g_all = _dev_f32(grad_color, "grad_color"), _dev_f32(grad_allmap, "grad_allmap")
         else:
             g_color, g_all = grad_color, grad_allmap
-        cs = _settings_struct(rs, keep, out_plane=getattr(ctx, "out_plane", 0), grad_plane=gp)
-
         b = getattr(ctx, "bwd_bufs", None)
         if b is None:      # P == 0, or backward called twice (retain_graph): allocate here
-            b = _grad_buffers(lib, dev, P, M, has_sh, has_colors, has_scales, has_cov)
+            b = _grad_buffers(lib, dev, P, M, has_sh, has_colors, has_scales, has_cov, defer_sh=getattr(ctx, "defer_sh", False))
         ctx.bwd_bufs = None
         ctx.grad_bucket = b["bucket"]
+        defer = b["defer_sh"]
+        cs = _settings_struct(rs, keep, out_plane=getattr(ctx, "out_plane", 0), grad_plane=gp, defer_sh=defer)
+        # deferred SH gradient: the caller (surfel_parallel._BandFrame) reduces the bucket and then calls expand()
+        ctx.sh_expand = None
+        if defer:
+            d_col_t, d_sh_t, campos_t = b["d_colors"], b["d_sh"], keep[3]
+
+            def expand():
+                with torch.cuda.device(dev):
+                    _cabi.check(lib.surfel_sh_grad_expand(P, M, int(rs.sh_degree), means3D.data_ptr(), campos_t.data_ptr(),
+                                                          d_col_t.data_ptr(), d_sh_t.data_ptr(),
+                                                          torch.cuda.current_stream(dev).cuda_stream))
+            ctx.sh_expand = expand
         d_means2D, d_opacity, d_means3D = b["d_means2D"], b["d_opacity"], b["d_means3D"]
         d_colors, d_cov, d_sh, d_scales, d_rot, scratch = b["d_colors"], b["d_cov"], b["d_sh"], b["d_scales"], b["d_rot"], b["scratch"]
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -337,7 +355,7 @@ class _RasterizeGaussians(torch.autograd.Function):
                 _ptr(d_cov), _ptr(d_sh), _ptr(d_scales), _ptr(d_rot), int(LOWPASS_DEPTH_QUIRK), stream))
         _mark("bwd_launched")
         # (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, settings)
-        return d_means3D, d_means2D, d_sh, d_colors, d_opacity, d_scales, d_rot, d_cov, None
+        return d_means3D, d_means2D, d_sh, (d_colors if has_colors else None), d_opacity, d_scales, d_rot, d_cov, None
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,

@@ -23,7 +23,7 @@ class SurfelSettings(ctypes.Structure):
         ("tile_row_begin", ctypes.c_int32), ("tile_row_end", ctypes.c_int32),
         ("bg", c_void_p), ("viewmatrix", c_void_p), ("projmatrix", c_void_p), ("campos", c_void_p),
         ("out_plane_stride", ctypes.c_int64), ("grad_plane_stride", ctypes.c_int64),
-        ("out_replica_count", ctypes.c_int32), ("reserved0", ctypes.c_int32),
+        ("out_replica_count", ctypes.c_int32), ("sh_grad_deferred", ctypes.c_int32),
         ("out_replica_base", ctypes.c_uint64 * 8),
     ]
 
@@ -58,6 +58,7 @@ SIGNATURES = {
     "surfel_grad_scratch_floats": (c_int, []),
     "surfel_backward": (c_int, [ctypes.POINTER(SurfelSettings), c_int, c_int, c_uint32] + [c_void_p] * 5 + [c_int]
                         + [c_void_p] * 15 + [c_int, c_void_p]),
+    "surfel_sh_grad_expand": (c_int, [c_int, c_int, c_int] + [c_void_p] * 4 + [c_void_p]),
     "surfel_mark_visible": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "surfel_sort_temp_bytes": (c_size_t, [c_size_t]),
     "surfel_post_forward": (c_int, [c_int, c_int, c_float] + [c_void_p] * 6 + [c_void_p]),

@@ -184,6 +184,12 @@ def symmetric_frame(H: int, W: int, world: int, device, group=None, multicast: b
 _last = {"grad_bucket": None, "frame": None, "works": [], "fused_via": None}
 
 
+def last_sh_expand():
+    """Callable that fills shs.grad from the (reduced) colour gradients of the most recent tile-band backward,
+    or None when the SH gradient was not deferred."""
+    return _last.get("sh_expand")
+
+
 def last_exchange_buffers():
     """(padded frame, flat gradient bucket) of the most recent tile-band step in this process — for
     measurement code that wants to time the collectives on the real buffers."""
@@ -201,6 +207,9 @@ class _BandFrame(torch.autograd.Function):
         H, W = int(settings.image_height), int(settings.image_width)
         _mark("band_enter")
         band = equal_band(H, rank, world)
+        # the SH gradient (48 of the 61 floats per splat) is a rank-1 expansion of 3 numbers: the backward leaves
+        # it unexpanded, the 16-float bucket is reduced, and the expansion runs once on the sum
+        ctx.defer_sh = world > 1 and dist.is_initialized()
         fused = gather in ("fused", "fused_multicast") and world > 1 and dist.is_initialized()
         if fused:
             buf, reps, hdl = symmetric_frame(H, W, world, means3D.device, group, multicast=(gather == "fused_multicast"))
@@ -216,10 +225,14 @@ class _BandFrame(torch.autograd.Function):
                                                            scales, rotations, cov3Ds_precomp, rs)
         if world > 1 and dist.is_initialized():
             # radii (and so visibility_filter / max_radii2D downstream) are per-band partials: a splat's tile
-            # rect is clipped to the band before it is counted.  Reduced BEFORE the frame exchange is enqueued: the
-            # backend runs its collectives in order, so a blocking collective queued behind asynchronous gathers
-            # would make the current stream wait for them (measured: no overlap at all in the first async version).
+            # rect is clipped to the band before it is counted.  The MAX over the ranks goes into a COPY: the
+            # backward must keep seeing the band's own radii (its preprocess backward skips splats the band
+            # culled, whose forward records were never written).  Reduced BEFORE the frame exchange is enqueued:
+            # the backend runs its collectives in order, so a blocking collective queued behind asynchronous
+            # gathers would make the current stream wait for them.
+            radii_band, radii = radii, radii.clone()
             dist.all_reduce(radii, op=dist.ReduceOp.MAX, group=group)
+            ctx.mark_non_differentiable(radii)
         if fused:
             hdl.barrier(channel=0)          # every rank's band has landed in every replica
             _last["works"] = []
@@ -237,8 +250,13 @@ class _BandFrame(torch.autograd.Function):
         world, group, grad_reduce = ctx.band_meta
         grads = _RasterizeGaussians.backward(ctx, g_color, None, g_allmap)
         _last["grad_bucket"] = ctx.grad_bucket
+        _last["sh_expand"] = ctx.sh_expand
         if grad_reduce == "all_reduce" and world > 1 and dist.is_initialized():
             dist.all_reduce(ctx.grad_bucket, op=dist.ReduceOp.SUM, group=group)   # every gradient, one collective, in place
+        if ctx.sh_expand is not None and grad_reduce == "all_reduce":
+            ctx.sh_expand()                  # dL_dsh = basis (x) summed colour gradient
+        # grad_reduce == "none": the caller reduces last_exchange_buffers()[1] itself and then calls
+        # last_sh_expand()() — until then dL_dsh (shs.grad) is unwritten
         return grads[:8] + (None, None, None, None, None, None)
 
 
@@ -248,7 +266,10 @@ def rasterize_tile_band(rasterizer_cls, settings, rank: int, world: int, group=N
     frame on every rank ("render" (3,H,W), "allmap" (7,H,W): views of one padded tensor), "radii" reduced
     with MAX over the ranks, and the band this rank rendered.  Differentiable; with grad_reduce="all_reduce"
     (default) the gradients that reach the inputs are already summed over the ranks; "none" leaves this
-    band's partial sums (the caller reduces them, e.g. with a reduce-scatter for a sharded optimizer).
+    band's partial sums in the flat bucket `last_exchange_buffers()[1]` (the caller reduces it, e.g. with a
+    reduce-scatter for a sharded optimizer, and then runs `last_sh_expand()()` to produce shs.grad).
+    The bucket holds 16 floats per splat, not 61: the SH gradient is the rank-1 expansion basis(dir) (x) dL_dcolor
+    and is expanded AFTER the reduction (C ABI: sh_grad_deferred / surfel_sh_grad_expand).
 
     gather="async" only ENQUEUES the all-gathers: the rows of this rank's own band (result["band"]) are valid on
     the current stream at once, the other ranks' rows after result["wait"]() — so a loss that is local to the

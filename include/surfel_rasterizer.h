@@ -83,7 +83,11 @@ typedef struct surfel_settings {
      * is thereby done by the stores of the kernel that produces them; the caller only has to run a cross-GPU
      * barrier before any rank reads rows outside its own band.  0 = off (default). */
     int32_t out_replica_count;
-    int32_t reserved0;
+    /* Backward, SH inputs only.  1 = surfel_backward() does NOT write dL_dsh; instead dL_dcolors (P,3, required)
+     * receives the gradient of the splat's SH colour with the forward's clamp mask applied — the 3 numbers the
+     * (P,M,3) SH gradient is a rank-1 expansion of.  A multi-GPU caller sums those 3 floats per splat across
+     * ranks (16 floats per splat in all instead of 61) and then calls surfel_sh_grad_expand() once.  0 = off. */
+    int32_t sh_grad_deferred;
     uint64_t out_replica_base[SURFEL_MAX_OUT_REPLICAS];
 } surfel_settings_t;
 
@@ -168,6 +172,12 @@ int surfel_backward(const surfel_settings_t* s, int P, int M, uint32_t R, const 
                     float* dL_dmeans2D, float* dL_dcolors, float* dL_dopacity, float* dL_dmeans3D,
                     float* dL_dtransMat, float* dL_dsh, float* dL_dscales, float* dL_drotations,
                     int lowpass_depth_quirk, void* stream);
+
+/* dL_dsh (P,M,3) = basis_k(normalize(means3D - campos)) * dL_dcolors[c] for k < (sh_degree+1)^2, zero beyond:
+ * the expansion surfel_backward() skips when surfel_settings.sh_grad_deferred = 1.  Rows of splats whose
+ * colour gradient is exactly zero are zero. */
+int surfel_sh_grad_expand(int P, int M, int sh_degree, const float* means3D, const float* campos,
+                          const float* dL_dcolors, float* dL_dsh, void* stream);
 
 /* GaussianRasterizer.markVisible: near-plane test (present: P bytes, 0/1). */
 int surfel_mark_visible(int P, const float* means3D, const float* viewmatrix,

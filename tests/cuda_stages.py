@@ -127,8 +127,12 @@ class CudaPipeline:
                     accum=i[offs[0]:offs[0] + 12 * n].view(np.float32).reshape(3, H, W).copy(),
                     n_contrib=i[offs[1]:offs[1] + 8 * n].view(np.uint32).reshape(2, H, W).copy())
 
-    def backward(self, dL_dcolor, dL_dothers, lowpass_quirk=True):
+    def backward(self, dL_dcolor, dL_dothers, lowpass_quirk=True, defer_sh=False):
+        """defer_sh: surfel_settings.sh_grad_deferred = 1 (dL_dsh left to surfel_sh_grad_expand, which is then
+        run here on the kernel's clamp-masked colour gradients; dL_dshs is poisoned first, so a row the expansion
+        misses cannot pass)."""
         lib, P, M = self.lib, self.P, self.M
+        self.cs.sh_grad_deferred = int(bool(defer_sh))
         gc, go = _t(dL_dcolor), _t(dL_dothers)
         e = lambda *s: torch.full(s, float("nan"), device="cuda")
         scratch = e(max(P, 1), lib.surfel_grad_scratch_floats())
@@ -144,6 +148,10 @@ class CudaPipeline:
             out["dL_dscales"].data_ptr() if self.scales is not None else None,
             out["dL_drotations"].data_ptr() if self.rotations is not None else None,
             int(lowpass_quirk), self.stream))
+        self.cs.sh_grad_deferred = 0
+        if defer_sh and M:
+            _cabi.check(lib.surfel_sh_grad_expand(P, M, int(self.cs.sh_degree), self.means3D.data_ptr(), self.campos.data_ptr(),
+                                                  out["dL_dcolors"].data_ptr(), out["dL_dshs"].data_ptr(), self.stream))
         torch.cuda.synchronize()
         res = {k: v.cpu().numpy() for k, v in out.items()}
         res["grad_rec"] = scratch.cpu().numpy()

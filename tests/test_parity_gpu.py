@@ -169,6 +169,30 @@ def test_backward_parity(oracle, cuda_lib, case):
         grad_check(k, got[k], ref[k])
 
 
+@pytest.mark.parametrize("sh_degree", [0, 1, 2, 3])
+def test_deferred_sh_gradient_equals_direct(cuda_lib, sh_degree):
+    """surfel_settings.sh_grad_deferred + surfel_sh_grad_expand (what the multi-GPU tile-band path reduces across
+    ranks: 3 colour-gradient floats per splat instead of the 48-float SH gradient) reproduces the directly written
+    dL_dsh, leaves every other gradient bit-identical, and writes zero rows for culled splats."""
+    from cuda_stages import CudaPipeline
+    scene, cam = world_scene(**CASES[0])
+    bg = np.array([0.1, 0.2, 0.3], np.float32)
+    gc, go = S.make_cotangents(cam["W"], cam["H"], 5)
+    res = []
+    for defer in (False, True):
+        pipe = CudaPipeline(scene, cam, bg, sh_degree=sh_degree)
+        pipe.preprocess(); pipe.duplicate(); pipe.sort(); pipe.render()
+        res.append(pipe.backward(gc.numpy(), go.numpy(), defer_sh=defer))
+    direct, deferred = res
+    for k in ("dL_dmeans3D", "dL_dscales", "dL_drotations", "dL_dopacity", "dL_dmeans2D"):
+        np.testing.assert_array_equal(direct[k], deferred[k], err_msg=k)
+    assert np.isfinite(deferred["dL_dshs"]).all()
+    scale = np.abs(direct["dL_dshs"]).max()
+    np.testing.assert_allclose(deferred["dL_dshs"], direct["dL_dshs"], rtol=0, atol=2e-6 * scale)
+    ncoef = (sh_degree + 1) ** 2
+    assert (deferred["dL_dshs"][:, ncoef:] == 0).all(), "coefficients beyond the active degree must stay zero"
+
+
 def test_precomputed_inputs(oracle, cuda_lib):
     """cov3D_precomp (= precomputed T) and colors_precomp paths (reference
     gaussian_renderer/__init__.py:64-75, :91-95)."""
