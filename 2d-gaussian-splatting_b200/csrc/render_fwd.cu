@@ -140,14 +140,14 @@ __global__ void __launch_bounds__(256, SURFEL_FWD_BLOCKS) render_fwd_kernel(Rend
         }
     }
 
+    const float c0 = C0 + T * __ldg(p.bg + 0), c1 = C1 + T * __ldg(p.bg + 1), c2 = C2 + T * __ldg(p.bg + 2);
     if (inside) {
         const size_t HW = (size_t)p.H * p.W;
         const size_t pix = (size_t)py * p.W + px;
         p.accum[pix] = T; p.accum[HW + pix] = M1; p.accum[2 * HW + pix] = M2;
         p.n_contrib[pix] = last_contributor & 0x7FFFFFFFu; p.n_contrib[HW + pix] = median_contributor;
-        const size_t OP = p.out_plane;
-        const float c0 = C0 + T * __ldg(p.bg + 0), c1 = C1 + T * __ldg(p.bg + 1), c2 = C2 + T * __ldg(p.bg + 2);
         if (p.rep_count == 0) {
+            const size_t OP = p.out_plane;
             p.out_color[pix] = c0;
             p.out_color[OP + pix] = c1;
             p.out_color[2 * OP + pix] = c2;
@@ -158,24 +158,39 @@ __global__ void __launch_bounds__(256, SURFEL_FWD_BLOCKS) render_fwd_kernel(Rend
             p.out_others[(kChNormal + 2) * OP + pix] = N2;
             p.out_others[kChMidDepth * OP + pix] = median_depth;
             p.out_others[kChDistortion * OP + pix] = dist;
-        } else {
-            // Tile-band exchange fused into the producer: the band's pixels go straight to every replica of the
-            // frame — peer GPUs' memory over NVLink, or one NVSwitch multicast address that the switch fans out
-            // (a plain st.global to a multicast mapping IS multimem.st: same SASS) — fire-and-forget stores that
-            // overlap with the blending of the CTAs still running.  No all-gather follows; the caller runs a
-            // cross-GPU barrier before reading rows of other bands.
+        }
+    }
+    if (p.rep_count != 0) {
+        // Tile-band exchange fused into the producer: the band's pixels go straight to every replica of the
+        // frame — peer GPUs' memory over NVLink, or one NVSwitch multicast address that the switch fans out
+        // (a plain st.global to a multicast mapping IS multimem.st: same SASS) — fire-and-forget stores that
+        // overlap with the blending of the CTAs still running.  No all-gather follows; the caller runs a
+        // cross-GPU barrier before reading rows of other bands.
+        // The tile's ten planes are first transposed through shared memory (the record slab is dead by now) so
+        // that a warp's store covers two full 64-byte tile rows instead of four 32-byte footprint rows: remote
+        // writes are limited by the number of requests the receiving GPU can take, not by bytes (measured:
+        // ~225 GB/s inbound with 32-byte segments whatever the number of senders).
+        __syncthreads();                                   // every warp has left the hit loop
+        float* s_out = reinterpret_cast<float*>(smem_raw); // [plane][16][16]
+        const int o = ly * kBlockX + lx;
+        s_out[0 * 256 + o] = c0; s_out[1 * 256 + o] = c1; s_out[2 * 256 + o] = c2;
+        s_out[(3 + kChDepth) * 256 + o] = D; s_out[(3 + kChAlpha) * 256 + o] = 1.0f - T;
+        s_out[(3 + kChNormal + 0) * 256 + o] = N0; s_out[(3 + kChNormal + 1) * 256 + o] = N1;
+        s_out[(3 + kChNormal + 2) * 256 + o] = N2;
+        s_out[(3 + kChMidDepth) * 256 + o] = median_depth; s_out[(3 + kChDistortion) * 256 + o] = dist;
+        __syncthreads();
+        const int rx = tid & 15, ry = tid >> 4;            // row-major over the tile: a warp = two 16-pixel rows
+        const int gx2 = tx * kBlockX + rx, gy2 = ty * kBlockY + ry;
+        if (gx2 < p.W && gy2 < p.H) {
+            const size_t OP = p.out_plane;
+            const size_t pix2 = (size_t)gy2 * p.W + gx2;
+            float v[10];
+#pragma unroll
+            for (int c = 0; c < 10; c++) v[c] = s_out[c * 256 + tid];
             for (int r = 0; r < p.rep_count; r++) {
-                float* b = reinterpret_cast<float*>(p.rep_base[r]) + pix;
-                b[0] = c0;
-                b[OP] = c1;
-                b[2 * OP] = c2;
-                b[(3 + kChDepth) * OP] = D;
-                b[(3 + kChAlpha) * OP] = 1.0f - T;
-                b[(3 + kChNormal + 0) * OP] = N0;
-                b[(3 + kChNormal + 1) * OP] = N1;
-                b[(3 + kChNormal + 2) * OP] = N2;
-                b[(3 + kChMidDepth) * OP] = median_depth;
-                b[(3 + kChDistortion) * OP] = dist;
+                float* b = reinterpret_cast<float*>(p.rep_base[r]) + pix2;
+#pragma unroll
+                for (int c = 0; c < 10; c++) b[c * OP] = v[c];
             }
         }
     }

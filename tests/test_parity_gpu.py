@@ -184,11 +184,14 @@ def test_deferred_sh_gradient_equals_direct(cuda_lib, sh_degree):
         pipe.preprocess(); pipe.duplicate(); pipe.sort(); pipe.render()
         res.append(pipe.backward(gc.numpy(), go.numpy(), defer_sh=defer))
     direct, deferred = res
-    for k in ("dL_dmeans3D", "dL_dscales", "dL_drotations", "dL_dopacity", "dL_dmeans2D"):
-        np.testing.assert_array_equal(direct[k], deferred[k], err_msg=k)
-    assert np.isfinite(deferred["dL_dshs"]).all()
-    scale = np.abs(direct["dL_dshs"]).max()
-    np.testing.assert_allclose(deferred["dL_dshs"], direct["dL_dshs"], rtol=0, atol=2e-6 * scale)
+    # two separate backward runs: the float atomics of the render backward may land in a different order, so the
+    # comparison is to a few ulps of the tensor's scale, not bitwise
+    for k in ("dL_dmeans3D", "dL_dscales", "dL_drotations", "dL_dopacity", "dL_dmeans2D", "dL_dshs"):
+        assert np.isfinite(deferred[k]).all(), k
+        scale = np.abs(direct[k]).max()
+        diff = np.abs(deferred[k].astype(np.float64) - direct[k]).max()
+        print(f"{k}: max |deferred - direct| = {diff:.3e} (scale {scale:.3e})")
+        assert diff <= 4e-6 * scale, f"{k}: {diff:.3e} vs scale {scale:.3e}"
     ncoef = (sh_degree + 1) ** 2
     assert (deferred["dL_dshs"][:, ncoef:] == 0).all(), "coefficients beyond the active degree must stay zero"
 
