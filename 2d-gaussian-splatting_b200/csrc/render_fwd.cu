@@ -35,13 +35,16 @@ constexpr int kBatch = SURFEL_FWD_BATCH;          // multiple of 32
 constexpr int kGroups = kBatch / 32;
 constexpr int kFwdSmemBytes = kRecQuadsFwd * kBatch * 16 + 8 * kGroups * 4;
 
-__global__ void __launch_bounds__(256, SURFEL_FWD_BLOCKS) render_fwd_kernel(RenderParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+// The ten output values of one pixel, in frame-plane order (3 colour planes, then the 7 planes of allmap).
+struct PixelOut { float v[10]; };
+
+// One 16x16 tile, front to back.  Writes the backward's per-pixel state (accum, n_contrib) and returns the
+// pixel's outputs; where they are stored is the caller's business.
+__device__ __forceinline__ void render_tile(const RenderParams& p, unsigned char* smem_raw, const int tx, const int ty, PixelOut& out) {
     float4* s_rec = reinterpret_cast<float4*>(smem_raw);                                   // [quad][slot]
     uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem_raw + kRecQuadsFwd * kBatch * 16);  // [warp][group], bit-reversed
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tx = blockIdx.x, ty = blockIdx.y + p.row0;
     int lx, ly;
     warp_pixel(warp, lane, lx, ly);
     const int px = tx * kBlockX + lx, py = ty * kBlockY + ly;
@@ -140,53 +143,90 @@ __global__ void __launch_bounds__(256, SURFEL_FWD_BLOCKS) render_fwd_kernel(Rend
         }
     }
 
-    const float c0 = C0 + T * __ldg(p.bg + 0), c1 = C1 + T * __ldg(p.bg + 1), c2 = C2 + T * __ldg(p.bg + 2);
     if (inside) {
         const size_t HW = (size_t)p.H * p.W;
         const size_t pix = (size_t)py * p.W + px;
         p.accum[pix] = T; p.accum[HW + pix] = M1; p.accum[2 * HW + pix] = M2;
         p.n_contrib[pix] = last_contributor & 0x7FFFFFFFu; p.n_contrib[HW + pix] = median_contributor;
-        if (p.rep_count == 0) {
-            const size_t OP = p.out_plane;
-            p.out_color[pix] = c0;
-            p.out_color[OP + pix] = c1;
-            p.out_color[2 * OP + pix] = c2;
-            p.out_others[kChDepth * OP + pix] = D;
-            p.out_others[kChAlpha * OP + pix] = 1.0f - T;
-            p.out_others[(kChNormal + 0) * OP + pix] = N0;
-            p.out_others[(kChNormal + 1) * OP + pix] = N1;
-            p.out_others[(kChNormal + 2) * OP + pix] = N2;
-            p.out_others[kChMidDepth * OP + pix] = median_depth;
-            p.out_others[kChDistortion * OP + pix] = dist;
-        }
     }
-    if (p.rep_count != 0) {
-        // Tile-band exchange fused into the producer: the band's pixels go straight to every replica of the
-        // frame — peer GPUs' memory over NVLink, or one NVSwitch multicast address that the switch fans out
-        // (a plain st.global to a multicast mapping IS multimem.st: same SASS) — fire-and-forget stores that
-        // overlap with the blending of the CTAs still running.  No all-gather follows; the caller runs a
-        // cross-GPU barrier before reading rows of other bands.
-        // The tile's ten planes are first transposed through shared memory (the record slab is dead by now) so
-        // that a warp's store covers two full 64-byte tile rows instead of four 32-byte footprint rows: remote
-        // writes are limited by the number of requests the receiving GPU can take, not by bytes (measured:
-        // ~225 GB/s inbound with 32-byte segments whatever the number of senders).
-        __syncthreads();                                   // every warp has left the hit loop
-        float* s_out = reinterpret_cast<float*>(smem_raw); // [plane][16][16]
-        const int o = ly * kBlockX + lx;
-        s_out[0 * 256 + o] = c0; s_out[1 * 256 + o] = c1; s_out[2 * 256 + o] = c2;
-        s_out[(3 + kChDepth) * 256 + o] = D; s_out[(3 + kChAlpha) * 256 + o] = 1.0f - T;
-        s_out[(3 + kChNormal + 0) * 256 + o] = N0; s_out[(3 + kChNormal + 1) * 256 + o] = N1;
-        s_out[(3 + kChNormal + 2) * 256 + o] = N2;
-        s_out[(3 + kChMidDepth) * 256 + o] = median_depth; s_out[(3 + kChDistortion) * 256 + o] = dist;
-        __syncthreads();
-        const int rx = tid & 15, ry = tid >> 4;            // row-major over the tile: a warp = two 16-pixel rows
-        const int gx2 = tx * kBlockX + rx, gy2 = ty * kBlockY + ry;
-        if (gx2 < p.W && gy2 < p.H) {
-            const size_t OP = p.out_plane;
+    out.v[0] = C0 + T * __ldg(p.bg + 0); out.v[1] = C1 + T * __ldg(p.bg + 1); out.v[2] = C2 + T * __ldg(p.bg + 2);
+    out.v[3 + kChDepth] = D; out.v[3 + kChAlpha] = 1.0f - T;
+    out.v[3 + kChNormal + 0] = N0; out.v[3 + kChNormal + 1] = N1; out.v[3 + kChNormal + 2] = N2;
+    out.v[3 + kChMidDepth] = median_depth; out.v[3 + kChDistortion] = dist;
+}
+
+__global__ void __launch_bounds__(256, SURFEL_FWD_BLOCKS) render_fwd_kernel(RenderParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tx = blockIdx.x, ty = blockIdx.y + p.row0;
+    PixelOut o;
+    render_tile(p, smem_raw, tx, ty, o);
+    int lx, ly;
+    warp_pixel(threadIdx.x >> 5, threadIdx.x & 31, lx, ly);
+    const int px = tx * kBlockX + lx, py = ty * kBlockY + ly;
+    if (px < p.W && py < p.H) {
+        const size_t OP = p.out_plane;
+        const size_t pix = (size_t)py * p.W + px;
+        p.out_color[pix] = o.v[0];
+        p.out_color[OP + pix] = o.v[1];
+        p.out_color[2 * OP + pix] = o.v[2];
+#pragma unroll
+        for (int c = 0; c < 7; c++) p.out_others[c * OP + pix] = o.v[3 + c];
+    }
+}
+
+// Tile-band exchange fused into the producer (surfel_settings.out_replica_base): the band's pixels go straight to
+// every replica of the frame — peer GPUs' memory over NVLink, or one NVSwitch multicast address that the switch
+// fans out (a plain st.global to a multicast mapping IS multimem.st: same SASS) — fire-and-forget stores that
+// overlap with the blending of the CTAs still running.  No all-gather follows; the caller runs a cross-GPU
+// barrier before reading rows of other bands.
+// Remote writes are limited by the number of REQUESTS the receiving GPU can take, not by bytes (measured at
+// N = 2 / 8: ~225 GB/s inbound with the 32-byte rows of a warp footprint whatever the number of senders, twice
+// that with 64-byte tile rows).  So one CTA renders TWO horizontally adjacent tiles, parks their outputs in
+// shared memory (the first tile's beside the record slab, the second's in the slab once it is dead), and every
+// warp store then covers one full 128-byte row of the 32-pixel strip.
+constexpr int kPairOutBytes = 10 * 256 * 4;                       // one tile's ten planes
+constexpr int kFwdPairSmemBytes = kFwdSmemBytes + kPairOutBytes;
+
+__global__ void __launch_bounds__(256, SURFEL_FWD_BLOCKS) render_fwd_pair_kernel(RenderParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s_a = reinterpret_cast<float*>(smem_raw + kFwdSmemBytes);     // first tile  [plane][16][16]
+    float* s_b = reinterpret_cast<float*>(smem_raw);                      // second tile, over the dead slab
+    const int tid = threadIdx.x;
+    const int tx0 = blockIdx.x * 2, ty = blockIdx.y + p.row0;
+    const bool two = tx0 + 1 < p.gx;
+    int lx, ly;
+    warp_pixel(tid >> 5, tid & 31, lx, ly);
+    const int o16 = ly * kBlockX + lx;
+    {
+        PixelOut o;
+        render_tile(p, smem_raw, tx0, ty, o);
+#pragma unroll
+        for (int c = 0; c < 10; c++) s_a[c * 256 + o16] = o.v[c];
+    }
+    __syncthreads();                                   // every warp has left the first tile's slab
+    if (two) {
+        PixelOut o;
+        render_tile(p, smem_raw, tx0 + 1, ty, o);
+        __syncthreads();                               // ... and the second's
+#pragma unroll
+        for (int c = 0; c < 10; c++) s_b[c * 256 + o16] = o.v[c];
+    }
+    __syncthreads();
+    // warp w writes rows w and w + 8 of the strip: lane = pixel x of the 32-pixel row
+    const int lane = tid & 31, warp = tid >> 5;
+    const int gx2 = tx0 * kBlockX + lane;
+    const float* src = lane < 16 ? s_a : s_b;
+    const int sx = lane & 15;
+    const size_t OP = p.out_plane;
+    if (gx2 < p.W && (lane < 16 || two)) {
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int ry = warp + 8 * h, gy2 = ty * kBlockY + ry;
+            if (gy2 >= p.H) continue;
             const size_t pix2 = (size_t)gy2 * p.W + gx2;
             float v[10];
 #pragma unroll
-            for (int c = 0; c < 10; c++) v[c] = s_out[c * 256 + tid];
+            for (int c = 0; c < 10; c++) v[c] = src[c * 256 + ry * kBlockX + sx];
             for (int r = 0; r < p.rep_count; r++) {
                 float* b = reinterpret_cast<float*>(p.rep_base[r]) + pix2;
 #pragma unroll
@@ -203,11 +243,12 @@ int launch_render_fwd(const RenderParams& p, cudaStream_t stream) {
     const int slot = current_device_slot();
     if (slot < 0 || !attr_set[slot]) {
         SURFEL_CUDA_OK(cudaFuncSetAttribute(render_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdSmemBytes));
+        SURFEL_CUDA_OK(cudaFuncSetAttribute(render_fwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFwdPairSmemBytes));
         if (slot >= 0) attr_set[slot] = true;
     }
-    dim3 grid(p.gx, rows);
     LaunchScope scope(kStRenderFwd, stream);
-    render_fwd_kernel<<<grid, 256, kFwdSmemBytes, stream>>>(p);
+    if (p.rep_count > 0) render_fwd_pair_kernel<<<dim3((p.gx + 1) / 2, rows), 256, kFwdPairSmemBytes, stream>>>(p);
+    else                 render_fwd_kernel<<<dim3(p.gx, rows), 256, kFwdSmemBytes, stream>>>(p);
     SURFEL_CUDA_OK(cudaGetLastError());
     return 0;
 }
