@@ -253,9 +253,9 @@ class _BandFrame(torch.autograd.Function):
         _last["sh_expand"] = ctx.sh_expand
         if grad_reduce == "all_reduce" and world > 1 and dist.is_initialized():
             dist.all_reduce(ctx.grad_bucket, op=dist.ReduceOp.SUM, group=group)   # every gradient, one collective, in place
-        if ctx.sh_expand is not None and grad_reduce == "all_reduce":
-            ctx.sh_expand()                  # dL_dsh = basis (x) summed colour gradient
-        # grad_reduce == "none": the caller reduces last_exchange_buffers()[1] itself and then calls
+        if ctx.sh_expand is not None and grad_reduce != "defer":
+            ctx.sh_expand()                  # dL_dsh = basis (x) colour gradient (summed over the ranks after "all_reduce")
+        # grad_reduce == "defer": the caller reduces last_exchange_buffers()[1] itself and then calls
         # last_sh_expand()() — until then dL_dsh (shs.grad) is unwritten
         return grads[:8] + (None, None, None, None, None, None)
 
@@ -266,8 +266,9 @@ def rasterize_tile_band(rasterizer_cls, settings, rank: int, world: int, group=N
     frame on every rank ("render" (3,H,W), "allmap" (7,H,W): views of one padded tensor), "radii" reduced
     with MAX over the ranks, and the band this rank rendered.  Differentiable; with grad_reduce="all_reduce"
     (default) the gradients that reach the inputs are already summed over the ranks; "none" leaves this
-    band's partial sums in the flat bucket `last_exchange_buffers()[1]` (the caller reduces it, e.g. with a
-    reduce-scatter for a sharded optimizer, and then runs `last_sh_expand()()` to produce shs.grad).
+    band's partial sums; "defer" additionally leaves shs.grad UNWRITTEN: the caller reduces the flat bucket
+    `last_exchange_buffers()[1]` itself (e.g. with a reduce-scatter for a sharded optimizer) and then runs
+    `last_sh_expand()()` to produce shs.grad from the reduced colour gradients.
     The bucket holds 16 floats per splat, not 61: the SH gradient is the rank-1 expansion basis(dir) (x) dL_dcolor
     and is expanded AFTER the reduction (C ABI: sh_grad_deferred / surfel_sh_grad_expand).
 
@@ -284,8 +285,8 @@ def rasterize_tile_band(rasterizer_cls, settings, rank: int, world: int, group=N
     returned views belong to a ring of two frames and stay valid until the second-next fused call.
     `rasterizer_cls` is accepted for symmetry with the single-GPU call and is not used."""
     del rasterizer_cls
-    if grad_reduce not in ("all_reduce", "none"):
-        raise ValueError("grad_reduce must be 'all_reduce' or 'none'")
+    if grad_reduce not in ("all_reduce", "none", "defer"):
+        raise ValueError("grad_reduce must be 'all_reduce', 'none' or 'defer'")
     if gather not in ("sync", "async", "fused", "fused_multicast"):
         raise ValueError("gather must be 'sync', 'async', 'fused' or 'fused_multicast'")
     empty = torch.Tensor([])

@@ -280,7 +280,7 @@ def tile_band_leg(rank, world, dev, steps=6, warmup=2, workload="config5"):
         for t in list(leaf.values()) + [m2d]:
             t.grad = None
         ev[0].record()
-        res = SP.rasterize_tile_band(GaussianRasterizer, rs, rank, world, grad_reduce="none", means3D=leaf["means3D"],
+        res = SP.rasterize_tile_band(GaussianRasterizer, rs, rank, world, grad_reduce="defer", means3D=leaf["means3D"],
                                      means2D=m2d, shs=leaf["shs"], opacities=leaf["opacities"], scales=leaf["scales"],
                                      rotations=leaf["rotations"])
         ev[1].record()                                                       # band forward + in-place all-gathers
@@ -328,7 +328,7 @@ def tile_band_leg(rank, world, dev, steps=6, warmup=2, workload="config5"):
         for t in list(leaf.values()) + [m2d]:
             t.grad = None
         ev[0].record()
-        res = SP.rasterize_tile_band(GaussianRasterizer, rs, rank, world, grad_reduce="none", gather=gather,
+        res = SP.rasterize_tile_band(GaussianRasterizer, rs, rank, world, grad_reduce="defer", gather=gather,
                                      means3D=leaf["means3D"], means2D=m2d, shs=leaf["shs"], opacities=leaf["opacities"],
                                      scales=leaf["scales"], rotations=leaf["rotations"])
         ev[1].record()
