@@ -50,7 +50,7 @@ def _newer(target, deps):
 def build(force=False, verbose=False):
     os.makedirs(LIB_DIR, exist_ok=True)
     os.makedirs(OBJ_DIR, exist_ok=True)
-    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h", ".inc"))]
     headers.append(os.path.join(HERE, "..", "include", "surfel_rasterizer.h"))
     objs, procs = [], []
     for src, extra in SOURCES.items():

@@ -35,114 +35,35 @@ constexpr int kBatch = SURFEL_FWD_BATCH;          // multiple of 32
 constexpr int kGroups = kBatch / 32;
 constexpr int kFwdSmemBytes = kRecQuadsFwd * kBatch * 16 + 8 * kGroups * 4;
 
+__global__ void __launch_bounds__(256, SURFEL_FWD_BLOCKS) render_fwd_kernel(RenderParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tx = blockIdx.x, ty = blockIdx.y + p.row0;
+#include "render_fwd_tile.inc"
+    if (inside) {
+        const size_t HW = (size_t)p.H * p.W;
+        const size_t pix = (size_t)py * p.W + px;
+        p.accum[pix] = T; p.accum[HW + pix] = M1; p.accum[2 * HW + pix] = M2;
+        p.n_contrib[pix] = last_contributor & 0x7FFFFFFFu; p.n_contrib[HW + pix] = median_contributor;
+        const size_t OP = p.out_plane;
+        p.out_color[pix] = C0 + T * __ldg(p.bg + 0);
+        p.out_color[OP + pix] = C1 + T * __ldg(p.bg + 1);
+        p.out_color[2 * OP + pix] = C2 + T * __ldg(p.bg + 2);
+        p.out_others[kChDepth * OP + pix] = D;
+        p.out_others[kChAlpha * OP + pix] = 1.0f - T;
+        p.out_others[(kChNormal + 0) * OP + pix] = N0;
+        p.out_others[(kChNormal + 1) * OP + pix] = N1;
+        p.out_others[(kChNormal + 2) * OP + pix] = N2;
+        p.out_others[kChMidDepth * OP + pix] = median_depth;
+        p.out_others[kChDistortion * OP + pix] = dist;
+    }
+}
+
 // The ten output values of one pixel, in frame-plane order (3 colour planes, then the 7 planes of allmap).
 struct PixelOut { float v[10]; };
 
-// One 16x16 tile, front to back.  Writes the backward's per-pixel state (accum, n_contrib) and returns the
-// pixel's outputs; where they are stored is the caller's business.
+// One tile for the pair kernel below: the same blend, the backward's per-pixel state written, outputs returned.
 __device__ __forceinline__ void render_tile(const RenderParams& p, unsigned char* smem_raw, const int tx, const int ty, PixelOut& out) {
-    float4* s_rec = reinterpret_cast<float4*>(smem_raw);                                   // [quad][slot]
-    uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem_raw + kRecQuadsFwd * kBatch * 16);  // [warp][group], bit-reversed
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int lx, ly;
-    warp_pixel(warp, lane, lx, ly);
-    const int px = tx * kBlockX + lx, py = ty * kBlockY + ly;
-    const bool inside = px < p.W && py < p.H;
-    const float pxf = (float)px, pyf = (float)py;
-    const float ox = (float)(tx * kBlockX), oy = (float)(ty * kBlockY);
-
-    const uint2 range = p.ranges[ty * p.gx + tx];
-    const int total = (int)(range.y - range.x);
-    const uint32_t rec_base = smem_u32(s_rec);
-    const uint32_t mask_base = smem_u32(s_mask) + (uint32_t)warp * (kGroups * 4);
-    constexpr float kMScale = kFar / (kFar - kNear);
-
-    float T = 1.0f, C0 = 0, C1 = 0, C2 = 0, N0 = 0, N1 = 0, N2 = 0, D = 0, M1 = 0, M2 = 0, dist = 0;
-    float median_depth = 0;
-    uint32_t last_contributor = inside ? 0u : 0x80000000u;   // top bit: this pixel is finished
-    uint32_t median_contributor = 0xFFFFFFFFu;
-    bool warp_done = __all_sync(0xffffffffu, !inside);
-
-    for (int base = 0; base < total; base += kBatch) {
-        // CTA-wide early out (also orders the previous round's smem reads before this refill)
-        if (base > 0 && !__syncthreads_or(!warp_done)) break;
-
-        const int n = min(kBatch, total - base);
-        // ---- stage + classify: thread t takes slots t, t + 256, ... (whole warps stay together) ----
-#pragma unroll
-        for (int k = 0; k < (kBatch + 255) / 256; k++) {
-            const int slot = k * 256 + tid;
-            if (k * 256 + (warp << 5) >= n) break;                       // warp-uniform
-            uint32_t m8 = 0;
-            if (slot < n) {
-                const uint32_t id = __ldg(p.point_list + range.x + base + slot);
-                const float4* r = p.rec + (size_t)id * kRecQuads;
-                const float4 bb = __ldg(r + 6), dg = __ldg(r + 7);
-#ifdef SURFEL_STAGE_LDG
-#pragma unroll
-                for (int q = 0; q < kRecQuadsFwd; q++) s_rec[q * kBatch + slot] = __ldg(r + q);
-#else
-#pragma unroll
-                for (int q = 0; q < kRecQuadsFwd; q++) cp_async16(rec_base + (uint32_t)(q * kBatch + slot) * 16u, r + q);
-#endif
-                m8 = classify_footprints(bb, dg, ox, oy);
-            }
-            uint32_t keep = 0;
-#pragma unroll
-            for (int w = 0; w < 8; w++) {
-                const uint32_t b = __ballot_sync(0xffffffffu, (m8 >> w) & 1u);
-                if (lane == w) keep = b;
-            }
-            // bit 31 = first slot of the group: taking the highest set bit first walks the hits front to back
-            if (lane < 8) s_mask[lane * kGroups + k * 8 + warp] = __brev(keep);
-        }
-        cp_async_wait_all();
-        __syncthreads();
-
-        if (!warp_done) {
-            const int ngroups = (n + 31) >> 5;
-            for (int g = 0; g < ngroups; g++) {
-                unsigned m = lds32u(mask_base + (uint32_t)g * 4u);
-                // The hit loop holds no warp-synchronous operation, so finished pixels simply skip it
-                // and a pixel that saturates leaves it early.  "Finished" is the top bit of
-                // last_contributor (lists are far shorter than 2^31).
-                if ((int)last_contributor >= 0) {
-                    const uint32_t g31 = rec_base + (uint32_t)(g * 32 + 31) * 16u;
-                    const uint32_t k32 = (uint32_t)(base + g * 32 + 32);
-                    while (m) {
-                        const uint32_t hb = high_bit(m);               // slot g*32 + 31 - hb
-                        m &= low_mask(hb);
-                        const uint32_t ra = g31 - hb * 16u;
-                        const float4 q0 = lds128(ra), q1 = lds128(ra + kBatch * 16), q2 = lds128(ra + 2 * kBatch * 16);
-                        PairEval e;
-                        if (!eval_pair(pxf, pyf, q0, q1, q2, e)) continue;
-                        const float4 q3 = lds128(ra + 3 * kBatch * 16), q4 = lds128(ra + 4 * kBatch * 16);
-                        // ray-splat depth = w of the intersection = det T / p.z; low-pass branch: Tw.z
-                        const float depth = (e.rho3d <= e.rho2d) ? q4.w * e.inv_pz : q3.w;
-                        if (q2.w < 0.0f && depth < kNear) continue;    // flagged splats only (warp-uniform flag)
-                        const float test_T = T * (1.0f - e.alpha);
-                        if (test_T < kTMin) { last_contributor |= 0x80000000u; break; }
-                        const uint32_t contributor = k32 - hb;   // 1-based list position
-                        const float w = e.alpha * T;
-                        const float A = 1.0f - T;
-                        const float mm = fmaf(fast_rcp(depth), -kMScale * kNear, kMScale);
-                        dist = fmaf(fmaf(mm, fmaf(mm, A, -(M1 + M1)), M2), w, dist);     // (mm^2 A + M2 - 2 mm M1) w
-                        D += depth * w;
-                        M1 += mm * w;
-                        M2 += mm * mm * w;
-                        if (T > 0.5f) { median_depth = depth; median_contributor = contributor; }
-                        N0 += q3.x * w; N1 += q3.y * w; N2 += q3.z * w;
-                        C0 += q4.x * w; C1 += q4.y * w; C2 += q4.z * w;
-                        T = test_T;
-                        last_contributor = contributor;
-                    }
-                }
-                if (__all_sync(0xffffffffu, (int)last_contributor < 0)) { warp_done = true; break; }
-            }
-        }
-    }
-
+#include "render_fwd_tile.inc"
     if (inside) {
         const size_t HW = (size_t)p.H * p.W;
         const size_t pix = (size_t)py * p.W + px;
@@ -153,25 +74,6 @@ __device__ __forceinline__ void render_tile(const RenderParams& p, unsigned char
     out.v[3 + kChDepth] = D; out.v[3 + kChAlpha] = 1.0f - T;
     out.v[3 + kChNormal + 0] = N0; out.v[3 + kChNormal + 1] = N1; out.v[3 + kChNormal + 2] = N2;
     out.v[3 + kChMidDepth] = median_depth; out.v[3 + kChDistortion] = dist;
-}
-
-__global__ void __launch_bounds__(256, SURFEL_FWD_BLOCKS) render_fwd_kernel(RenderParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int tx = blockIdx.x, ty = blockIdx.y + p.row0;
-    PixelOut o;
-    render_tile(p, smem_raw, tx, ty, o);
-    int lx, ly;
-    warp_pixel(threadIdx.x >> 5, threadIdx.x & 31, lx, ly);
-    const int px = tx * kBlockX + lx, py = ty * kBlockY + ly;
-    if (px < p.W && py < p.H) {
-        const size_t OP = p.out_plane;
-        const size_t pix = (size_t)py * p.W + px;
-        p.out_color[pix] = o.v[0];
-        p.out_color[OP + pix] = o.v[1];
-        p.out_color[2 * OP + pix] = o.v[2];
-#pragma unroll
-        for (int c = 0; c < 7; c++) p.out_others[c * OP + pix] = o.v[3 + c];
-    }
 }
 
 // Tile-band exchange fused into the producer (surfel_settings.out_replica_base): the band's pixels go straight to

@@ -487,6 +487,14 @@ def run_ours(args, rank, local_rank, world):
     ms_arr, cnt_arr = (ctypes.c_double * n_stage)(), (ctypes.c_int * n_stage)()
     launches0 = lib.surfel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # Python's cyclic garbage collector is paused inside the timed regions: a generation-2 pass over the heap of
+    # a process that has torch and a 1 M-splat scene loaded takes ~7-9 ms, i.e. five steps' worth of a 20-step
+    # window on whichever rank it hits (seen as one 8.4-8.8 ms host interval at N = 2 and N = 8,
+    # profiles/r2_bench_8gpu_b.json).  The op itself creates no reference cycles (tests/test_parity_gpu.py::
+    # test_out_buffers_are_not_kept_alive_by_the_graph runs with the collector off), so nothing accumulates.
+    import gc as _gc
+    _gc.collect()
+    _gc.disable()
     sampler.mark_start()
     host_ts = [time.perf_counter()]          # diagnostic only: when the host finished issuing each step
     e0.record()
@@ -496,6 +504,7 @@ def run_ours(args, rank, local_rank, world):
     e1.record()
     torch.cuda.synchronize()
     sampler.mark_stop()
+    _gc.enable()
     launches = int(lib.surfel_launch_count() - launches0)
     # second pass, same loop, with CUDA events recorded around every kernel on the launching stream:
     # per-kernel durations for the roofline (kept out of the pass that produces `value`)
@@ -584,10 +593,12 @@ def run_ours(args, rank, local_rank, world):
         barrier()
         e2e_steps = max(4, min(args.steps, 50))     # >= 4 so that the 3-stage pipeline reaches steady state
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        _gc.collect(); _gc.disable()
         ea.record(pipe.s_in)
         pipe.run(e2e_steps, host_in, host_gc, host_go, host_out, host_grad)
         eb.record(pipe.s_out)
         torch.cuda.synchronize()
+        _gc.enable()
         te = torch.tensor([ea.elapsed_time(eb)], device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -654,7 +665,8 @@ def run_ours(args, rank, local_rank, world):
             "config": {"workload": workload_string(args.workload, P, W, H),
                        "visible": V, "instances": R, "parallelism": f"view-parallel x{world} (no collective)",
                        "host_numa_node": numa_node, "pinned_buffers": "interleaved over NUMA nodes" if pin_interleaved else "local to the GPU's NUMA node",
-                       "l2_policy": "inputs larger than L2 (232 MB of splat parameters + 83 MB of outputs per step vs 126 MB L2)"},
+                       "l2_policy": "inputs larger than L2 (232 MB of splat parameters + 83 MB of outputs per step vs 126 MB L2)",
+                       "host_gc": "python cyclic garbage collector paused inside the timed regions (collected right before)"},
             "e2e": e2e, "gpu_launches": launches, "gpu_launches_per_step": launches / args.steps,
             "roofline": roofline, "clocks": clocks, "host_step_ms": host_step_ms,
         }
