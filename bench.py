@@ -67,20 +67,41 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (20 ms period; every line
-    is stamped on receipt so that only samples inside [mark_start, mark_stop] are reported)."""
+    """SM clock / throttle reasons sampled DURING the timed region; every sample is stamped on receipt so that only
+    samples inside [mark_start, mark_stop] are reported.  Source: NVML in-process (nvidia_ml_py: the same counters
+    nvidia-smi prints — SM clock and the event-reason bit mask only, two cheap calls every 10 ms, no power / SMBus reads); fallback: the profiling recipe's `nvidia-smi --query-gpu
+    ... -lms 200` child process.  Round 2 measured what the sampler itself costs: `nvidia-smi -lms 20` (round 1's
+    setting) stalled kernel launches for 2-13 ms a few times per 100 steps — 561 / 603 / 621 Msplats/s in three
+    back-to-back runs against 624 without any sampler (profiles/r2_bench_repeat_*.json)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index, self.proc, self.lines, self.t0, self.t1 = index, None, [], None, None
+        self.mode, self._stop = None, False
 
     def start(self):
+        want = os.environ.get("SURFEL_BENCH_CLOCKS", "nvml")
+        if want == "nvml":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+                self.nv = pynvml
+                self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+                self.mode = "nvml"
+                self.t = threading.Thread(target=self._poll_nvml, daemon=True)
+                self.t.start()
+                return
+            except Exception:
+                self.mode = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.mode = "nvidia-smi -lms 200"
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
             t_end = time.time() + 3.0
@@ -88,6 +109,20 @@ class ClockSampler:
                 time.sleep(0.01)
         except Exception:
             self.proc = None
+
+    def _poll_nvml(self):
+        nv = self.nv
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        while not self._stop:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = int(get_reasons(self.h))
+                flags = ",".join("Active" if r & bits[n] else "Not Active" for n in self.NAMES)
+                self.lines.append((time.time(), f"{sm}, {self.mx}, 0, {flags}"))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -100,15 +135,17 @@ class ClockSampler:
         self.t1 = time.time()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.05)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            pass
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no clock sampler (NVML and nvidia-smi unavailable, or SURFEL_BENCH_NOCLOCKS)"]}
+        time.sleep(0.06)
+        self._stop = True
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+        names = self.NAMES
 
         def parse(lines):
             sm, mx, reasons = [], [], set()
@@ -131,7 +168,7 @@ class ClockSampler:
             note = "timed region shorter than 2 sampling periods: samples within +-0.3 s of it (GPU busy with the same loop)"
         sm, mx, reasons = parse(inside)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons), "note": note}
+                "samples": len(sm), "reasons": sorted(reasons), "note": note, "source": self.mode}
 
 
 def bind_to_gpu_numa_node(index):
