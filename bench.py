@@ -524,11 +524,12 @@ def run_ours(args, rank, local_rank, world):
     ms_arr, cnt_arr = (ctypes.c_double * n_stage)(), (ctypes.c_int * n_stage)()
     launches0 = lib.surfel_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # Python's cyclic garbage collector is paused inside the timed regions: a generation-2 pass over the heap of
-    # a process that has torch and a 1 M-splat scene loaded takes ~7-9 ms, i.e. five steps' worth of a 20-step
-    # window on whichever rank it hits (seen as one 8.4-8.8 ms host interval at N = 2 and N = 8,
-    # profiles/r2_bench_8gpu_b.json).  The op itself creates no reference cycles (tests/test_parity_gpu.py::
-    # test_out_buffers_are_not_kept_alive_by_the_graph runs with the collector off), so nothing accumulates.
+    # Python's cyclic garbage collector is paused inside the timed regions (collected right before): a
+    # generation-2 pass over the heap of a process with torch and a 1 M-splat scene loaded takes milliseconds, i.e.
+    # several steps' worth of a 20-step window on whichever rank it hits.  A precaution — the host stalls actually
+    # seen in round 2 came from the nvidia-smi clock sampler (see ClockSampler).  The op itself creates no
+    # reference cycles (tests/test_parity_gpu.py::test_out_buffers_are_not_kept_alive_by_the_graph runs with the
+    # collector off), so nothing accumulates.
     import gc as _gc
     _gc.collect()
     _gc.disable()
