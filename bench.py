@@ -531,8 +531,10 @@ def run_ours(args, rank, local_rank, world):
     # reference cycles (tests/test_parity_gpu.py::test_out_buffers_are_not_kept_alive_by_the_graph runs with the
     # collector off), so nothing accumulates.
     import gc as _gc
-    _gc.collect()
-    _gc.disable()
+    pause_gc = not os.environ.get("SURFEL_BENCH_KEEP_GC")
+    if pause_gc:
+        _gc.collect()
+        _gc.disable()
     sampler.mark_start()
     host_ts = [time.perf_counter()]          # diagnostic only: when the host finished issuing each step
     e0.record()
@@ -631,7 +633,8 @@ def run_ours(args, rank, local_rank, world):
         barrier()
         e2e_steps = max(4, min(args.steps, 50))     # >= 4 so that the 3-stage pipeline reaches steady state
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        _gc.collect(); _gc.disable()
+        if pause_gc and not os.environ.get("SURFEL_BENCH_E2E_KEEP_GC"):
+            _gc.collect(); _gc.disable()
         ea.record(pipe.s_in)
         pipe.run(e2e_steps, host_in, host_gc, host_go, host_out, host_grad)
         eb.record(pipe.s_out)
