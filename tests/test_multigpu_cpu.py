@@ -124,3 +124,15 @@ def test_band_helpers():
         assert all(b[1] - b[0] <= rp for b in eb) and SP.padded_frame(1, H, 8, world, "cpu").shape[1] == rp * world * 16
     x = torch.arange(2 * 40 * 8, dtype=torch.float32).reshape(2, 40, 8)
     assert torch.equal(SP.gather_band_outputs(x, 40, 0, 1), x)
+
+
+def test_rasterize_tile_band_rejects_unknown_modes():
+    """Argument validation happens before anything touches a device."""
+    import surfel_parallel as SP
+    with pytest.raises(ValueError):
+        SP.rasterize_tile_band(None, None, 0, 1, grad_reduce="sum")
+    with pytest.raises(ValueError):
+        SP.rasterize_tile_band(None, None, 0, 1, gather="nccl")
+    with pytest.raises(Exception, match="excatly one"):
+        SP.rasterize_tile_band(None, None, 0, 1, means3D=torch.zeros(1, 3), means2D=torch.zeros(1, 3), opacities=torch.zeros(1, 1))
+
