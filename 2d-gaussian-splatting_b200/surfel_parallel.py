@@ -230,7 +230,7 @@ class _BandFrame(torch.autograd.Function):
             # culled, whose forward records were never written).  Reduced BEFORE the frame exchange is enqueued:
             # the backend runs its collectives in order, so a blocking collective queued behind asynchronous
             # gathers would make the current stream wait for them.
-            radii_band, radii = radii, radii.clone()
+            radii = radii.clone()          # the context keeps the band's own tensor (saved by the op's forward)
             dist.all_reduce(radii, op=dist.ReduceOp.MAX, group=group)
             ctx.mark_non_differentiable(radii)
         if fused:

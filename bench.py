@@ -311,7 +311,6 @@ def tile_band_leg(rank, world, dev, steps=6, warmup=2, workload="config5"):
     gc, go = gc.to(dev), go.to(dev)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(8)]
     acc = [0.0] * 6
-    acc_ov = {"all_reduce": 0.0, "reduce_scatter": 0.0}
 
     def step(timed):
         for t in list(leaf.values()) + [m2d]:
@@ -397,7 +396,6 @@ def tile_band_leg(rank, world, dev, steps=6, warmup=2, workload="config5"):
     t_host = (_time.perf_counter() - t_host) / steps * 1e3
     lib.surfel_profile_enable(0); lib.surfel_profile_read(ms_arr, cnt_arr)
     kernels = {lib.surfel_profile_stage_name(i).decode(): round(ms_arr[i] / steps, 3) for i in range(nst) if cnt_arr[i]}
-    bucket_divisible = SP.last_exchange_buffers()[1].numel() % world == 0
     # (gather="async" — NCCL gathers hidden behind the backward — was measured and dropped from the default run:
     # 9.2 vs 8.9 ms at N = 2, 10.7 vs 5.6 ms at N = 8; profiles/r2_bench_8gpu_a.json)
     variants = [("fused", "all_reduce", "fused"), ("fused_multicast", "all_reduce", "fused_multicast")]
