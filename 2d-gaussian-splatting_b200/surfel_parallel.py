@@ -181,6 +181,12 @@ def symmetric_frame(H: int, W: int, world: int, device, group=None, multicast: b
     return buf, reps, hdl
 
 
+def release_symmetric_frames() -> None:
+    """Drops the cached symmetric frames (two per frame shape and group; 2 x 1.3 GB for an 8K frame).  Collective in
+    effect: every rank should call it at the same point, after its last use of a fused frame."""
+    _sym_frames.clear()
+
+
 _last = {"grad_bucket": None, "frame": None, "works": [], "fused_via": None}
 
 
