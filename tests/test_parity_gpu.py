@@ -357,6 +357,43 @@ def test_tile_band_rows_match_full_frame(oracle, cuda_lib):
         grad_check(k + " (sum of bands)", acc[k], gfull[k], rtol=1e-3)
 
 
+@pytest.mark.parametrize("W,H", [(640, 360), (333, 200)])
+def test_replicated_output_path_on_one_gpu(cuda_lib, W, H):
+    """The tile-band exchange fused into the render kernel (out_replicas -> render_fwd_pair_kernel: two tiles per
+    CTA, 128-byte rows stored to every replica) exercised on ONE GPU: the replicas are two local frames.  Both
+    must equal the plain kernel's frame bit for bit — including an odd number of tile columns (333 px = 21 tiles:
+    the last CTA of a row owns a single tile) and a ragged right / bottom edge — and rows outside the rendered
+    band must stay untouched."""
+    from diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    dev = torch.device("cuda", 0)
+    P = 20_000
+    cam = S.make_camera(W, H)
+    scene = S.make_scene(P, W, H, 33)
+    rs = GaussianRasterizationSettings(
+        image_height=H, image_width=W, tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"], bg=torch.tensor([0.1, 0.2, 0.3], device=dev),
+        scale_modifier=1.0, viewmatrix=cam["viewmatrix"].to(dev), projmatrix=cam["projmatrix"].to(dev), sh_degree=3,
+        campos=cam["campos"].to(dev), prefiltered=False, debug=False)
+    inp = {k: scene[k].to(dev) for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+    m2d = torch.zeros(P, 3, device=dev)
+    with torch.no_grad():
+        color, radii, allmap = GaussianRasterizer(rs)(means2D=m2d, **inp)
+        gy = (H + 15) // 16
+        for band in ((0, gy), (1, max(2, gy - 1))):
+            a = torch.full((10, H + 7, W), -7.0, device=dev)          # plane stride larger than H*W
+            b = torch.full((10, H + 7, W), -7.0, device=dev)
+            local = torch.full((10, H + 7, W), -7.0, device=dev)      # out_buffers: NOT written in replica mode
+            rs2 = rs._replace(tile_rows=band, out_buffers=(local[:3, :H], local[3:, :H]), out_replicas=(a.data_ptr(), b.data_ptr()))
+            c2, r2, m2 = GaussianRasterizer(rs2)(means2D=m2d, **inp)
+            torch.cuda.synchronize()
+            ys = slice(band[0] * 16, min(H, band[1] * 16))
+            for rep in (a, b):
+                assert torch.equal(rep[:3, ys], color[:, ys]) and torch.equal(rep[3:, ys], allmap[:, ys])
+                outside = torch.ones(H + 7, dtype=torch.bool, device=dev)
+                outside[ys] = False
+                assert bool((rep[:, outside] == -7.0).all()), "rows outside the band were written"
+            assert bool((local == -7.0).all()), "replica mode must not write the local out_buffers"
+
+
 def test_out_buffers_are_not_kept_alive_by_the_graph(cuda_lib):
     """Rendering into caller-owned `out_buffers` (the tile-band path) must not create a reference cycle between
     the outputs and the autograd context: after the results of a step are dropped, its frame, workspaces and
