@@ -136,3 +136,8 @@ def test_rasterize_tile_band_rejects_unknown_modes():
     with pytest.raises(Exception, match="excatly one"):
         SP.rasterize_tile_band(None, None, 0, 1, means3D=torch.zeros(1, 3), means2D=torch.zeros(1, 3), opacities=torch.zeros(1, 1))
 
+
+def test_tile_band_example_compiles():
+    import py_compile
+    py_compile.compile(os.path.join(ROOT, "examples", "tile_band_step.py"), doraise=True)
+
