@@ -52,6 +52,18 @@ def main():
             lanes = g[4] / g[2] if g[2] else 0.0
             print(f"| {key} | {g[0]} | {g[1]:.0f} | {100 * g[1] * warps / total_i:.1f} % | {lanes:.1f} | {100 * g[3] / max(total_s, 1):.1f} % |")
         print()
+        # where the warps wait: stall reasons summed over the kernel's instructions (all samples)
+        reasons = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+        tot = {h: 0 for h in reasons}
+        for r in data:
+            for h in reasons:
+                try:
+                    tot[h] += int(r[ix[h]])
+                except (ValueError, IndexError):
+                    pass
+        allr = sum(tot.values()) or 1
+        top = sorted(tot.items(), key=lambda kv: -kv[1])[:8]
+        print("Stall samples by reason: " + ", ".join(f"{h[6:]} {100 * v / allr:.1f} %" for h, v in top) + "\n")
 
 
 if __name__ == "__main__":
